@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) tokenize/detokenize path behind the `audiocodecs` Codec API.
+
+Drop-in for `audiocodecs.{Encodec,DAC,Mimi}` `sig_to_toks` / `toks_to_sig` (R/audiocodecs/codec.py:57-66,90-100).
+"""
+from .codec import Codec
+from .encodec import Encodec
+
+__version__ = "0.1.0"
+__all__ = ["Codec", "Encodec"]

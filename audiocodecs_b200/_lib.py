@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI shared library (include/audiocodecs_b200.h).
+
+There is NO fallback: if the library is missing or a symbol is absent this module raises, and every
+op in this package goes through it.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaudiocodecs_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "audiocodecs_b200.h")
+
+c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+
+class AcConvF32(ctypes.Structure):
+    """mirror of `struct ac_conv_f32`"""
+    _fields_ = [
+        ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("alpha", c_vp), ("res", c_vp), ("y", c_vp), ("vlen", c_vp),
+        ("x_bstride", c_i64), ("y_bstride", c_i64), ("res_bstride", c_i64),
+        ("x_rstride", c_i32),
+        ("batch", c_i32), ("x_rows", c_i32), ("cin", c_i32), ("m_rows", c_i32), ("n_cols", c_i32),
+        ("taps", c_i32), ("stride", c_i32), ("dilation", c_i32), ("pad_left", c_i32),
+        ("pad_mode", c_i32), ("reflect_len", c_i32), ("act", c_i32), ("epi", c_i32),
+        ("out_shift", c_i64), ("out_valid", c_i64),
+    ]
+
+
+def declared_symbols():
+    """Every `AC_API` entry point the public header declares."""
+    with open(HEADER_PATH) as f:
+        return re.findall(r"AC_API\s+[\w\s\*]+?\b(ac_\w+)\s*\(", f.read())
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"audiocodecs_b200: CUDA library not built ({LIB_PATH}). Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C audiocodecs_b200/csrc`. There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name in declared_symbols():
+            if not hasattr(L, name):
+                raise RuntimeError(f"audiocodecs_b200: {LIB_PATH} does not export {name}")
+        L.ac_last_error.restype = ctypes.c_char_p
+        L.ac_launch_count.restype = c_i64
+        L.ac_abi_version.restype = c_i32
+        L.ac_conv1d_f32.argtypes = [ctypes.POINTER(AcConvF32), c_vp]
+        L.ac_lstm_layer_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
+        L.ac_rvq_encode_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_rvq_decode_f32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
+        L.ac_resample_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ac_last_error().decode(errors="replace")
+        raise RuntimeError(f"audiocodecs_b200: {what} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().ac_launch_count())

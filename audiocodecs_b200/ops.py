@@ -1,0 +1,180 @@
+"""Host-side launch helpers: torch tensors (device memory + stream only) -> C-ABI calls.
+
+Activations are channels-last `[B, L, C]` fp32 tensors.  Nothing here computes on the host or
+falls back to torch ops; a CPU tensor raises.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import AcConvF32
+
+PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
+ACT_NONE, ACT_ELU, ACT_SNAKE = 0, 1, 2
+EPI_NONE, EPI_TANH, EPI_GELU = 0, 1, 2
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("audiocodecs_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback. "
+                               "Move the codec and its inputs with .to('cuda').")
+
+
+class ConvSpec:
+    """One packed convolution / transposed convolution / linear layer.
+
+    w: [taps, cin, n_cols] fp32 (see packing.py), bias [n_cols] or None.
+    geometry: 'causal' (EnCodec/Mimi: left pad K_eff-stride, right pad to ceil(L/stride)),
+              'same'   (DAC: symmetric zero padding `padding`, floor length rule),
+              'tr'     (transposed, kernel 2*stride; `tr_pad` = torch padding, causal trim when 0)
+    """
+
+    def __init__(self, w, bias, *, cout, kernel=1, stride=1, dilation=1, geometry="causal", pad_mode=PAD_ZERO,
+                 padding=0, act=ACT_NONE, alpha=None, epi=EPI_NONE, tr_stride=0, tr_pad=0):
+        self.w, self.bias, self.alpha = w, bias, alpha
+        self.cout, self.kernel, self.stride, self.dilation = cout, kernel, stride, dilation
+        self.geometry, self.pad_mode, self.padding = geometry, pad_mode, padding
+        self.act, self.epi, self.tr_stride, self.tr_pad = act, epi, tr_stride, tr_pad
+        self.taps, self.cin, self.n_cols = w.shape
+
+    def apply(self, fn):
+        """module.to()/cuda() support: Codec._apply maps `fn` over the packed tensors."""
+        self.w = fn(self.w)
+        self.bias = fn(self.bias) if self.bias is not None else None
+        self.alpha = fn(self.alpha) if self.alpha is not None else None
+
+    def out_len(self, L):
+        if self.geometry == "causal":
+            return -(-L // self.stride)
+        if self.geometry == "same":
+            k_eff = (self.kernel - 1) * self.dilation + 1
+            return (L + 2 * self.padding - k_eff) // self.stride + 1
+        s = self.tr_stride
+        return (L - 1) * s - 2 * self.tr_pad + 2 * s if self.tr_pad else L * s
+
+
+def conv(spec: ConvSpec, x: torch.Tensor, res: torch.Tensor = None, out: torch.Tensor = None,
+         vlen: torch.Tensor = None) -> torch.Tensor:
+    """x [B, L, Cin] -> y [B, Lout, Cout] (+res). `res` may alias `out`."""
+    _need_cuda(x, spec.w, res, out)
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.stride(2) == 1 and x.shape[2] == spec.cin, (x.shape, spec.cin)
+    B, L, _ = x.shape
+    Lout = spec.out_len(L)
+    if Lout <= 0:
+        raise ValueError(f"input too short for this layer (L={L})")
+    if out is None:
+        out = torch.empty((B, Lout, spec.cout), device=x.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (B, Lout, spec.cout)
+    p = AcConvF32()
+    p.x, p.w, p.bias, p.alpha = x.data_ptr(), spec.w.data_ptr(), _ptr(spec.bias), _ptr(spec.alpha)
+    p.res, p.y, p.vlen = _ptr(res), out.data_ptr(), _ptr(vlen)
+    if res is not None:
+        assert res.shape == out.shape and res.is_contiguous()
+    p.x_bstride, p.y_bstride, p.res_bstride = x.stride(0), out.stride(0), (res.stride(0) if res is not None else 0)
+    p.x_rstride = x.stride(1)
+    p.batch, p.x_rows, p.cin, p.n_cols, p.taps = B, L, spec.cin, spec.n_cols, spec.taps
+    p.act, p.epi, p.pad_mode = spec.act, spec.epi, spec.pad_mode
+    p.reflect_len = L
+    p.out_valid = Lout * spec.cout
+    if spec.geometry == "tr":
+        p.stride, p.dilation, p.pad_left = 1, 1, 1
+        p.m_rows = L + 1 if spec.tr_pad else L
+        p.out_shift = spec.tr_pad * spec.cout
+        p.pad_mode = PAD_ZERO
+    else:
+        k_eff = (spec.kernel - 1) * spec.dilation + 1
+        p.stride, p.dilation, p.m_rows, p.out_shift = spec.stride, spec.dilation, Lout, 0
+        if spec.geometry == "causal":
+            p.pad_left = k_eff - spec.stride
+            extra = (Lout - 1) * spec.stride + k_eff - p.pad_left - L
+            m = max(p.pad_left, extra)
+            if spec.pad_mode == PAD_REFLECT and L <= m:
+                p.reflect_len = m + 1  # the reference zero-extends tiny inputs first (HF/encodec:148-155)
+        else:
+            p.pad_left = spec.padding
+    _lib.check(_lib.lib().ac_conv1d_f32(ctypes.byref(p), _stream()), "ac_conv1d_f32")
+    return out
+
+
+def lstm_layer(pre, w_hh, skip, sync_ws):
+    """pre [B,T,4C] -> h [B,T,C] (+skip)."""
+    _need_cuda(pre, w_hh, skip)
+    B, T, C4 = pre.shape
+    C = C4 // 4
+    out = torch.empty((B, T, C), device=pre.device, dtype=torch.float32)
+    assert pre.is_contiguous() and w_hh.is_contiguous() and (skip is None or skip.is_contiguous())
+    _lib.check(_lib.lib().ac_lstm_layer_f32(_ptr(pre), _ptr(w_hh), _ptr(skip), _ptr(out), B, T, C, _ptr(sync_ws), _stream()),
+               "ac_lstm_layer_f32")
+    return out
+
+
+def rvq_encode(x, codebooks, cb_norm, codes_out, stages, code_offset=0, metric=0, residual_out=None):
+    """x [rows, D] fp32; codebooks [S, C, D]; writes codes_out[rows, Ktot] int64 columns code_offset..+stages."""
+    _need_cuda(x, codebooks, cb_norm, codes_out)
+    rows, D = x.shape
+    assert x.is_contiguous() and codes_out.dtype == torch.int64 and codes_out.is_contiguous()
+    _lib.check(_lib.lib().ac_rvq_encode_f32(_ptr(x), _ptr(codebooks), _ptr(cb_norm), _ptr(codes_out), _ptr(residual_out),
+                                            rows, D, codebooks.shape[1], stages, codes_out.shape[-1], code_offset, metric,
+                                            _stream()), "ac_rvq_encode_f32")
+    return codes_out
+
+
+def rvq_decode(codes, codebooks, stages, code_offset=0, err_flag=None):
+    """codes [rows, Ktot] int64 -> [rows, D] fp32."""
+    _need_cuda(codes, codebooks)
+    rows = codes.shape[0]
+    D = codebooks.shape[2]
+    assert codes.dtype == torch.int64 and codes.is_contiguous()
+    out = torch.empty((rows, D), device=codes.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ac_rvq_decode_f32(_ptr(codes), _ptr(codebooks), _ptr(out), rows, D, codebooks.shape[1], stages,
+                                            codes.shape[-1], code_offset, _ptr(err_flag), _stream()), "ac_rvq_decode_f32")
+    return out
+
+
+_TAPS_CACHE = {}
+
+
+def resample_taps(orig_freq, new_freq, device):
+    """Windowed-sinc polyphase taps, built once per (orig,new) pair (the reference rebuilds them per
+    call, TA/functional.py:1305-1402).  Index arithmetic in fp32 exactly as torchaudio does for fp32
+    waveforms; this is setup-time host math on a few hundred floats, not the data path."""
+    key = (orig_freq, new_freq, str(device))
+    if key not in _TAPS_CACHE:
+        g = math.gcd(int(orig_freq), int(new_freq))
+        o, n = int(orig_freq) // g, int(new_freq) // g
+        base = min(o, n) * 0.99
+        width = math.ceil(6 * o / base)
+        idx = torch.arange(-width, width + o, dtype=torch.float32)[None] / o
+        t = torch.arange(0, -n, -1, dtype=torch.float32)[:, None] / n + idx
+        t = (t * base).clamp(-6, 6)
+        window = torch.cos(t * math.pi / 6 / 2) ** 2
+        t = t * math.pi
+        taps = torch.where(t == 0, torch.tensor(1.0), t.sin() / t) * window * (base / o)
+        _TAPS_CACHE[key] = (taps.contiguous().to(device), width, o, n)
+    return _TAPS_CACHE[key]
+
+
+def resample(sig, orig_freq, new_freq):
+    """sig [B,T] fp32 -> [B, ceil(new*T/orig)] ; identity when the rates match (TA:1473-1474)."""
+    if orig_freq == new_freq:
+        return sig
+    _need_cuda(sig)
+    taps, width, o, n = resample_taps(orig_freq, new_freq, sig.device)
+    B, T = sig.shape
+    sig = sig.contiguous().float()
+    out_len = int(torch.ceil(torch.as_tensor(n * T / o)).long())  # TA:1426 (fp32 rounding before ceil)
+    out = torch.empty((B, out_len), device=sig.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ac_resample_f32(_ptr(sig), _ptr(taps), _ptr(out), B, T, out_len, o, n, taps.shape[1], width,
+                                          _stream()), "ac_resample_f32")
+    return out

@@ -1,0 +1,42 @@
+"""CPU: the C-ABI library is built in-tree, loads, and exports every symbol include/*.h declares."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from audiocodecs_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert {"ac_conv1d_f32", "ac_lstm_layer_f32", "ac_rvq_encode_f32", "ac_rvq_decode_f32", "ac_resample_f32"} <= set(names)
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+    assert _lib.lib().ac_abi_version() == 1
+
+
+def test_struct_mirror_matches_header_size():
+    # 7 pointers + 3 int64 + 14 int32 + 2 int64, natural alignment
+    assert ctypes.sizeof(_lib.AcConvF32) == 7 * 8 + 3 * 8 + 14 * 4 + 2 * 8
+
+
+def test_no_cpu_fallback(encodec_sd):
+    import audiocodecs_b200 as A
+    c = A.Encodec(24000, 24000, num_codebooks=8, state_dict=encodec_sd)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.sig_to_toks(torch.zeros(1, 2400))
+
+
+def test_constructor_contract(encodec_sd):
+    import audiocodecs_b200 as A
+    with pytest.raises(ValueError):
+        A.Encodec(24000, 24000, mode="bogus", state_dict=encodec_sd)
+    c = A.Encodec(16000, 24000, mode="encode", num_codebooks=4, state_dict=encodec_sd)
+    assert (c.sample_rate, c.orig_sample_rate, c.num_codebooks, c.vocab_size, c.mode) == (16000, 24000, 4, 1024, "encode")
+    assert not hasattr(c, "_dec")
+    bad = A.Encodec(24000, 24000, num_codebooks=3, state_dict=encodec_sd)
+    with pytest.raises(ValueError, match="bandwidth"):
+        bad._num_quantizers()

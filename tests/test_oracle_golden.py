@@ -1,0 +1,46 @@
+"""CPU: the oracle restatement reproduces the live reference's recorded outputs (tests/golden/, written by
+oracle/make_golden.py from the unmodified /root/reference wrappers)."""
+import pytest
+import torch
+
+from helpers import make_input
+from oracle import encodec_ref, resample_ref
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_encodec_oracle_matches_reference_golden(encodec_sd, encodec_golden, case):
+    c = encodec_golden["cases"][case]
+    sig = make_input(c["seed"], c["B"], c["T"])
+    length = None if c["length"] is None else torch.tensor(c["length"])
+    with torch.no_grad():
+        toks, gaps, _ = encodec_ref.sig_to_toks(encodec_sd, sig, c["K"], c["sample_rate"], 24000, length, return_gaps=True)
+        rec = encodec_ref.toks_to_sig(encodec_sd, c["toks"].long(), c["sample_rate"], 24000)
+    ref_toks = c["toks"].long()
+    assert toks.shape == ref_toks.shape and toks.dtype == torch.int64
+    safe = gaps > 1e-4
+    assert (toks == ref_toks)[safe].all(), "oracle codes differ from the reference away from near-ties"
+    assert (toks == ref_toks).float().mean() > 0.99
+    assert rec.shape == c["rec"].shape
+    assert (rec - c["rec"]).abs().max() <= 1e-4 * max(1.0, c["rec"].abs().max().item())
+
+
+def test_encodec_lstm_loop_equals_aten(encodec_sd):
+    x = torch.randn(2, 512, 9, generator=torch.Generator().manual_seed(3))
+    a = encodec_ref.lstm_block(encodec_sd, "encoder.layers.13", x)
+    b = encodec_ref.lstm_block_aten(encodec_sd, "encoder.layers.13", x)
+    assert (a - b).abs().max() < 1e-5
+
+
+def test_encodec_invalid_num_codebooks():
+    with pytest.raises(ValueError):
+        encodec_ref.num_quantizers_for(3)
+
+
+@pytest.mark.parametrize("o,n", [(16000, 24000), (24000, 16000), (16000, 44100), (44100, 16000)])
+def test_resample_oracle_matches_torchaudio(o, n):
+    torchaudio = pytest.importorskip("torchaudio")
+    x = make_input(5, 2, 4001)
+    ref = torchaudio.functional.resample(x, o, n)
+    got = resample_ref.resample(x, o, n)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() < 1e-6
