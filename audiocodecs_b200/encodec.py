@@ -29,6 +29,7 @@ class Encodec(Codec):
         if use_vocos:
             raise NotImplementedError("the Vocos decoder branch (R/audiocodecs/encodec.py:53-66) is outside this build")
         self.num_codebooks = num_codebooks
+        self.compute_dtype = "f32"
         self.use_vocos = use_vocos
         self.vocab_size = 1024
         tag = int(orig_sample_rate / 1000)

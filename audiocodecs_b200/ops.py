@@ -16,6 +16,42 @@ ACT_NONE, ACT_ELU, ACT_SNAKE = 0, 1, 2
 EPI_NONE, EPI_TANH, EPI_GELU = 0, 1, 2
 
 
+class Profiler:
+    """Per-launch device timing with CUDA events on the launching stream (bench.py roofline leg)."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, name, start, flops=0.0, bytes_=0.0):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.append((name, start, e, flops, bytes_))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e, fl, by in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += by
+            d["n"] += 1
+        return out
+
+
+_PROFILER = None
+
+
+def set_profiler(p):
+    global _PROFILER
+    _PROFILER = p
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -103,7 +139,12 @@ def conv(spec: ConvSpec, x: torch.Tensor, res: torch.Tensor = None, out: torch.T
                 p.reflect_len = m + 1  # the reference zero-extends tiny inputs first (HF/encodec:148-155)
         else:
             p.pad_left = spec.padding
+    t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_conv1d_f32(ctypes.byref(p), _stream()), "ac_conv1d_f32")
+    if _PROFILER:
+        # algorithmic work: 2 FLOP per MAC of the reference's dense op; fp32 activation bytes in+out
+        _PROFILER.end("conv1d_f32", t0, 2.0 * B * p.m_rows * spec.n_cols * spec.taps * spec.cin,
+                      4.0 * (x.numel() + out.numel() + spec.w.numel()))
     return out
 
 
@@ -114,8 +155,11 @@ def lstm_layer(pre, w_hh, skip, sync_ws):
     C = C4 // 4
     out = torch.empty((B, T, C), device=pre.device, dtype=torch.float32)
     assert pre.is_contiguous() and w_hh.is_contiguous() and (skip is None or skip.is_contiguous())
+    t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_lstm_layer_f32(_ptr(pre), _ptr(w_hh), _ptr(skip), _ptr(out), B, T, C, _ptr(sync_ws), _stream()),
                "ac_lstm_layer_f32")
+    if _PROFILER:
+        _PROFILER.end("lstm_layer_f32", t0, 2.0 * B * T * 4 * C * C, 4.0 * (pre.numel() + out.numel()))
     return out
 
 
@@ -124,9 +168,12 @@ def rvq_encode(x, codebooks, cb_norm, codes_out, stages, code_offset=0, metric=0
     _need_cuda(x, codebooks, cb_norm, codes_out)
     rows, D = x.shape
     assert x.is_contiguous() and codes_out.dtype == torch.int64 and codes_out.is_contiguous()
+    t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_rvq_encode_f32(_ptr(x), _ptr(codebooks), _ptr(cb_norm), _ptr(codes_out), _ptr(residual_out),
                                             rows, D, codebooks.shape[1], stages, codes_out.shape[-1], code_offset, metric,
                                             _stream()), "ac_rvq_encode_f32")
+    if _PROFILER:
+        _PROFILER.end("rvq_encode_f32", t0, 2.0 * rows * D * codebooks.shape[1] * stages, 4.0 * x.numel() + 8.0 * rows * stages)
     return codes_out
 
 
@@ -137,8 +184,11 @@ def rvq_decode(codes, codebooks, stages, code_offset=0, err_flag=None):
     D = codebooks.shape[2]
     assert codes.dtype == torch.int64 and codes.is_contiguous()
     out = torch.empty((rows, D), device=codes.device, dtype=torch.float32)
+    t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_rvq_decode_f32(_ptr(codes), _ptr(codebooks), _ptr(out), rows, D, codebooks.shape[1], stages,
                                             codes.shape[-1], code_offset, _ptr(err_flag), _stream()), "ac_rvq_decode_f32")
+    if _PROFILER:
+        _PROFILER.end("rvq_decode_f32", t0, 0.0, 8.0 * rows * stages + 4.0 * rows * D * (stages + 1))
     return out
 
 
