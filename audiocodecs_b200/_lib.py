@@ -24,7 +24,35 @@ class AcConvF32(ctypes.Structure):
         ("taps", c_i32), ("stride", c_i32), ("dilation", c_i32), ("pad_left", c_i32),
         ("pad_mode", c_i32), ("reflect_len", c_i32), ("act", c_i32), ("epi", c_i32),
         ("out_shift", c_i64), ("out_valid", c_i64),
+        ("x_is_bf16", c_i32), ("act2", c_i32), ("y_bf16", c_vp), ("y_act_bf16", c_vp),
+        ("y_bf16_bstride", c_i64), ("y_act_bstride", c_i64),
     ]
+
+
+class AcTcSrc(ctypes.Structure):
+    """mirror of `struct ac_tc_src`"""
+    _fields_ = [("base", c_vp), ("c0", c_i32), ("phases", c_i32), ("rows", c_i32),
+                ("phase_stride", c_i64), ("row_stride", c_i64), ("batch_stride", c_i64),
+                ("taps", c_i32), ("dilation", c_i32), ("shift", c_i32), ("lo_of", c_i32)]
+
+
+class AcConvTcDesc(ctypes.Structure):
+    """mirror of `struct ac_conv_tc_desc`"""
+    _fields_ = [("src", AcTcSrc * 4), ("n_src", c_i32), ("w", c_vp), ("w_split", c_i32), ("k_total", c_i32), ("n_total", c_i32),
+                ("bk", c_i32), ("bias", c_vp), ("alpha", c_vp), ("res", c_vp), ("y", c_vp), ("y_act", c_vp), ("y_lo", c_vp),
+                ("y_act_lo", c_vp), ("y32", c_vp),
+                ("act", c_i32), ("epi", c_i32), ("act_mod", c_i32),
+                ("y_bstride", c_i64), ("y_act_bstride", c_i64), ("y32_bstride", c_i64), ("res_bstride", c_i64),
+                ("out_shift", c_i64), ("out_valid", c_i64),
+                ("batch", c_i32), ("m_rows", c_i32), ("n_tile_hint", c_i32), ("grid_hint", c_i32)]
+
+
+class AcLstmDesc(ctypes.Structure):
+    """mirror of `struct ac_lstm_desc`"""
+    _fields_ = [("pre", c_vp), ("w_hh", c_vp), ("out", c_vp), ("out_bf16", c_vp), ("skip_bf16", c_vp), ("final_bf16", c_vp),
+                ("skip_bstride", c_i64), ("final_bstride", c_i64), ("final_act", c_i32),
+                ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("sync_ws", c_vp),
+                ("out_lo", c_vp), ("skip_lo", c_vp), ("final_lo", c_vp)]
 
 
 def declared_symbols():
@@ -55,6 +83,10 @@ def lib():
         L.ac_rvq_encode_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_rvq_decode_f32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_resample_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_lstm_layer.argtypes = [ctypes.POINTER(AcLstmDesc), c_vp]
+        L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
+        L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]
+        L.ac_pad_halo_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
         _lib = L
     return _lib
 

@@ -5,6 +5,8 @@
 // gathered with the layer's padding rule (zero / reflect / replicate) and the prologue activation
 // (ELU / Snake) is applied while staging, so padded copies and activated copies of the activation
 // tensors are never materialised (the reference materialises both: HF/encodec:160-162, :268).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -25,7 +27,13 @@ __device__ __forceinline__ int pad_index(int pos, int L, int mode, int reflect_l
     return pos;
 }
 
-template <int BM, int BN>
+template <bool BF>
+__device__ __forceinline__ float load_x(const void* base, int64_t idx) {
+    if (BF) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+    return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+
+template <int BM, int BN, bool XBF>
 __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p) {
     constexpr int TM = 4, TN = 4;
     static_assert((BM / TM) * (BN / TN) == THREADS, "tile/thread mismatch");
@@ -39,7 +47,7 @@ __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p
     const int tx = tid % (BN / TN);
     const int ty = tid / (BN / TN);
 
-    const float* __restrict__ xb = p.x + (int64_t)b * p.x_bstride;
+    const int64_t xoff = (int64_t)b * p.x_bstride;
     const int vlen = p.vlen ? p.vlen[b] : p.x_rows;
     const int Ktot = p.taps * p.cin;
 
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p
                 const int pos = m * p.stride + j * p.dilation - p.pad_left;
                 const int src = pad_index(pos, p.x_rows, p.pad_mode, p.reflect_len);
                 if (src >= 0 && src < vlen) {
-                    v = __ldg(xb + (int64_t)src * p.x_rstride + c);
+                    v = load_x<XBF>(p.x, xoff + (int64_t)src * p.x_rstride + c);
                     if (p.act == AC_ACT_ELU) v = ac::elu1(v);
                     else if (p.act == AC_ACT_SNAKE) v = ac::snake(v, __ldg(p.alpha + c));
                 } else if (p.act == AC_ACT_SNAKE || p.act == AC_ACT_ELU) {
@@ -97,7 +105,9 @@ __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p
     }
 
     // ---- epilogue: bias, activation, flat-shifted store (+ residual)
-    float* __restrict__ yb = p.y + (int64_t)b * p.y_bstride;
+    float* __restrict__ yb = p.y ? p.y + (int64_t)b * p.y_bstride : nullptr;
+    __nv_bfloat16* ybf = p.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(p.y_bf16) + (int64_t)b * p.y_bf16_bstride : nullptr;
+    __nv_bfloat16* yact = p.y_act_bf16 ? reinterpret_cast<__nv_bfloat16*>(p.y_act_bf16) + (int64_t)b * p.y_act_bstride : nullptr;
     const float* rb = p.res ? p.res + (int64_t)b * p.res_bstride : nullptr;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -113,7 +123,9 @@ __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p
             const int64_t flat = (int64_t)m * p.n_cols + n - p.out_shift;
             if (flat < 0 || flat >= p.out_valid) continue;
             if (rb) v += rb[flat];
-            yb[flat] = v;
+            if (yb) yb[flat] = v;
+            if (ybf) ybf[flat] = __float2bfloat16(v);
+            if (yact) yact[flat] = __float2bfloat16(p.act2 == AC_ACT_ELU ? ac::elu1(v) : v);
         }
     }
 }
@@ -121,18 +133,25 @@ __global__ void __launch_bounds__(THREADS) conv1d_f32_kernel(const ac_conv_f32 p
 }  // namespace
 
 extern "C" int ac_conv1d_f32(const ac_conv_f32* p, void* stream) {
-    AC_REQUIRE(p && p->x && p->w && p->y, "ac_conv1d_f32: null pointer");
+    AC_REQUIRE(p && p->x && p->w && (p->y || p->y_bf16 || p->y_act_bf16), "ac_conv1d_f32: null pointer");
     AC_REQUIRE(p->batch > 0 && p->m_rows > 0 && p->n_cols > 0 && p->taps > 0 && p->cin > 0,
                "ac_conv1d_f32: empty problem (batch %d rows %d cols %d)", p->batch, p->m_rows, p->n_cols);
     AC_REQUIRE(p->act != AC_ACT_SNAKE || p->alpha, "ac_conv1d_f32: snake needs alpha");
     AC_REQUIRE(p->batch <= 65535, "ac_conv1d_f32: batch %d > 65535", p->batch);
     cudaStream_t s = (cudaStream_t)stream;
+    const bool xbf = p->x_is_bf16 != 0;
     if (p->n_cols <= 16) {
         dim3 grid((p->m_rows + 255) / 256, (p->n_cols + 15) / 16, p->batch);
-        conv1d_f32_kernel<256, 16><<<grid, THREADS, 0, s>>>(*p);
+        if (xbf) conv1d_f32_kernel<256, 16, true><<<grid, THREADS, 0, s>>>(*p);
+        else conv1d_f32_kernel<256, 16, false><<<grid, THREADS, 0, s>>>(*p);
+    } else if (p->n_cols <= 32) {
+        dim3 grid((p->m_rows + 127) / 128, (p->n_cols + 31) / 32, p->batch);
+        if (xbf) conv1d_f32_kernel<128, 32, true><<<grid, THREADS, 0, s>>>(*p);
+        else conv1d_f32_kernel<128, 32, false><<<grid, THREADS, 0, s>>>(*p);
     } else {
         dim3 grid((p->m_rows + 63) / 64, (p->n_cols + 63) / 64, p->batch);
-        conv1d_f32_kernel<64, 64><<<grid, THREADS, 0, s>>>(*p);
+        if (xbf) conv1d_f32_kernel<64, 64, true><<<grid, THREADS, 0, s>>>(*p);
+        else conv1d_f32_kernel<64, 64, false><<<grid, THREADS, 0, s>>>(*p);
     }
     return ac::finish_launch("ac_conv1d_f32");
 }

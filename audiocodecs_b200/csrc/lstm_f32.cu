@@ -9,6 +9,7 @@
 // monotonic counter in global memory, not a grid-wide sync.  Co-residency of all CTAs is guaranteed
 // by a cooperative launch (which fails instead of dead-locking if the grid does not fit).
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -26,7 +27,11 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_layer_f32_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh, const float* __restrict__ skip,
-                      float* __restrict__ out, int batch, int steps, int C, int* sync_ws) {
+                      float* __restrict__ out, int batch, int steps, int C, int* sync_ws,
+                      __nv_bfloat16* __restrict__ out_bf, const __nv_bfloat16* __restrict__ skip_bf,
+                      __nv_bfloat16* __restrict__ final_bf, long long skip_bs, long long final_bs, int final_act,
+                      __nv_bfloat16* __restrict__ out_lo, const __nv_bfloat16* __restrict__ skip_lo,
+                      __nv_bfloat16* __restrict__ final_lo) {
     extern __shared__ __align__(16) float smem[];
     float4* Ws = reinterpret_cast<float4*>(smem);   // [C][HU] float4 = (i,f,g,o) rows for (k, unit)
     float* hs = smem + (size_t)C * HU * 4;          // [C][BB] previous hidden state, k-major
@@ -93,12 +98,32 @@ lstm_layer_f32_kernel(const float* __restrict__ pre, const float* __restrict__ w
         const float i_ = ac::sigmoidf_(gi), f_ = ac::sigmoidf_(gf), o_ = ac::sigmoidf_(go);
         c_state = f_ * c_state + i_ * tanhf(gg);
         const float h = o_ * tanhf(c_state);
-        if (live) out[((size_t)b * steps + t) * C + u] = h;
+        if (live) {
+            out[((size_t)b * steps + t) * C + u] = h;
+            if (out_bf) {
+                const __nv_bfloat16 hb = __float2bfloat16(h);
+                out_bf[((size_t)b * steps + t) * C + u] = hb;
+                if (out_lo) out_lo[((size_t)b * steps + t) * C + u] = __float2bfloat16(h - __bfloat162float(hb));
+            }
+        }
         __syncthreads();  // all h[t] of this CTA written (and hs reads finished)
         if (tid == 0) {
             __threadfence();
             atomicAdd(counter, 1);
         }
+    }
+    if (final_bf) {
+        // bf16 edge: final = act(h + skip); our own (b,u) column only, h values are still in `out`
+        if (live)
+            for (int t = 0; t < steps; ++t) {
+                float v = out[((size_t)b * steps + t) * C + u];
+                if (skip_bf) v += __bfloat162float(skip_bf[(size_t)b * skip_bs + (size_t)t * C + u]);
+                if (skip_lo) v += __bfloat162float(skip_lo[(size_t)b * skip_bs + (size_t)t * C + u]);
+                if (final_act == AC_ACT_ELU) v = ac::elu1(v);
+                const __nv_bfloat16 vb = __float2bfloat16(v);
+                final_bf[(size_t)b * final_bs + (size_t)t * C + u] = vb;
+                if (final_lo) final_lo[(size_t)b * final_bs + (size_t)t * C + u] = __float2bfloat16(v - __bfloat162float(vb));
+            }
     }
     if (skip) {
         // residual connection of EncodecLSTM: out = lstm(x) + x.  Only our own (b,u) column: no sync needed
@@ -119,8 +144,10 @@ lstm_layer_f32_kernel(const float* __restrict__ pre, const float* __restrict__ w
 
 }  // namespace
 
-extern "C" int ac_lstm_layer_f32(const float* pre, const float* w_hh, const float* skip, float* out,
-                                 int32_t batch, int32_t steps, int32_t hidden, int32_t* sync_ws, void* stream) {
+static int lstm_launch(const float* pre, const float* w_hh, const float* skip, float* out, int32_t batch, int32_t steps,
+                       int32_t hidden, int32_t* sync_ws, void* out_bf16, const void* skip_bf16, void* final_bf16,
+                       int64_t skip_bs, int64_t final_bs, int32_t final_act, void* stream, void* out_lo = nullptr,
+                       const void* skip_lo = nullptr, void* final_lo = nullptr) {
     AC_REQUIRE(pre && w_hh && out && sync_ws, "ac_lstm_layer_f32: null pointer");
     AC_REQUIRE(batch > 0 && steps > 0, "ac_lstm_layer_f32: empty problem");
     AC_REQUIRE(hidden % HU == 0 && hidden <= 1024, "ac_lstm_layer_f32: hidden %d must be a multiple of %d", hidden, HU);
@@ -146,10 +173,30 @@ extern "C" int ac_lstm_layer_f32(const float* pre, const float* w_hh, const floa
         const float* skip_w = skip ? skip + (size_t)b0 * steps * hidden : nullptr;
         float* out_w = out + (size_t)b0 * steps * hidden;
         int nb_ = nb, steps_ = steps, hid_ = hidden;
-        void* args[] = {(void*)&pre_w, (void*)&w_hh, (void*)&skip_w, (void*)&out_w, &nb_, &steps_, &hid_, (void*)&sync_ws};
+        __nv_bfloat16* obf = out_bf16 ? (__nv_bfloat16*)out_bf16 + (size_t)b0 * steps * hidden : nullptr;
+        const __nv_bfloat16* sbf = skip_bf16 ? (const __nv_bfloat16*)skip_bf16 + (size_t)b0 * skip_bs : nullptr;
+        __nv_bfloat16* fbf = final_bf16 ? (__nv_bfloat16*)final_bf16 + (size_t)b0 * final_bs : nullptr;
+        long long sbs = skip_bs, fbs = final_bs;
+        int fact = final_act;
+        __nv_bfloat16* olo = out_lo ? (__nv_bfloat16*)out_lo + (size_t)b0 * steps * hidden : nullptr;
+        const __nv_bfloat16* slo = skip_lo ? (const __nv_bfloat16*)skip_lo + (size_t)b0 * skip_bs : nullptr;
+        __nv_bfloat16* flo = final_lo ? (__nv_bfloat16*)final_lo + (size_t)b0 * final_bs : nullptr;
+        void* args[] = {(void*)&pre_w, (void*)&w_hh, (void*)&skip_w, (void*)&out_w, &nb_, &steps_, &hid_, (void*)&sync_ws,
+                        (void*)&obf, (void*)&sbf, (void*)&fbf, &sbs, &fbs, &fact, (void*)&olo, (void*)&slo, (void*)&flo};
         e = cudaLaunchCooperativeKernel((void*)lstm_layer_f32_kernel, dim3(n_ug, groups), dim3(THREADS), args, smem, s);
         ac::count_launch();
         if (e != cudaSuccess) { ac::set_error("ac_lstm_layer_f32: launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     return 0;
+}
+
+extern "C" int ac_lstm_layer_f32(const float* pre, const float* w_hh, const float* skip, float* out,
+                                 int32_t batch, int32_t steps, int32_t hidden, int32_t* sync_ws, void* stream) {
+    return lstm_launch(pre, w_hh, skip, out, batch, steps, hidden, sync_ws, nullptr, nullptr, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int ac_lstm_layer(const ac_lstm_desc* d, void* stream) {
+    AC_REQUIRE(d, "ac_lstm_layer: null descriptor");
+    return lstm_launch(d->pre, d->w_hh, nullptr, d->out, d->batch, d->steps, d->hidden, d->sync_ws, d->out_bf16, d->skip_bf16,
+                       d->final_bf16, d->skip_bstride, d->final_bstride, d->final_act, stream, d->out_lo, d->skip_lo, d->final_lo);
 }

@@ -5,13 +5,15 @@ Same constructor arguments and tensor shapes; the `transformers.EncodecModel` ar
 """
 import torch
 
-from . import ops, packing
+from . import ops, packing, tc
 from .codec import Codec
 from .ops import ACT_ELU, ACT_NONE, PAD_REFLECT, ConvSpec
+from .tc import Act, Src, TcWeights
 
 __all__ = ["Encodec"]
 
 RATIOS = (8, 5, 4, 2)  # facebook/encodec_24khz upsampling_ratios (HF/encodec/configuration_encodec.py)
+SPLIT_MIN_CH = 128     # activations with >= this many channels travel as (hi, lo) bf16 pairs (precision)
 _VALID_BW = (1.5, 3.0, 6.0, 12.0, 24.0)
 
 
@@ -24,12 +26,15 @@ class Encodec(Codec):
     """
 
     def __init__(self, sample_rate, orig_sample_rate=24000, mode="reconstruct", num_codebooks=8, use_vocos=False,
-                 state_dict=None):
+                 state_dict=None, precision="bf16"):
         super().__init__(sample_rate, orig_sample_rate, mode)
         if use_vocos:
             raise NotImplementedError("the Vocos decoder branch (R/audiocodecs/encodec.py:53-66) is outside this build")
         self.num_codebooks = num_codebooks
-        self.compute_dtype = "f32"
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
+        self.precision = precision
+        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
         self.use_vocos = use_vocos
         self.vocab_size = 1024
         tag = int(orig_sample_rate / 1000)
@@ -80,7 +85,7 @@ class Encodec(Codec):
         return layers
 
     def _build(self, sd):
-        self._specs = []
+        self._specs, self._tcw = [], []
         if self.mode != "decode":  # R/audiocodecs/encodec.py:67-71 drops the unused half
             enc = [self._conv(sd, "encoder.layers.0")]
             idx = 1
@@ -102,6 +107,13 @@ class Encodec(Codec):
                 idx += 3
             self._dec = dec
             self._dec_last = self._conv(sd, f"decoder.layers.{idx}", act=ACT_ELU)
+        if self.mode != "encode":
+            import copy
+            self._dec_last_noact = copy.copy(self._dec_last)
+            self._dec_last_noact.act = ACT_NONE
+            self._specs.append(self._dec_last_noact)
+        if self.precision == "bf16":
+            self._build_tc(sd)
         nq = sum(1 for k in sd if k.startswith("quantizer.layers.") and k.endswith(".codebook.embed"))
         cb = torch.stack([sd[f"quantizer.layers.{k}.codebook.embed"].float() for k in range(nq)]).contiguous()
         self.register_buffer("codebooks", cb, persistent=False)                 # [32, 1024, 128]
@@ -110,7 +122,129 @@ class Encodec(Codec):
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
 
     def _packed(self):
-        return self._specs
+        return self._specs + self._tcw
+
+    # ------------------------------------------------------------------ bf16 tensor-path packing
+    def _tc_conv(self, sd, prefix):
+        """Conv1d [Cout,Cin,K] -> bf16 [Cout][K*Cin] (column = tap*Cin + c; a stride-s/kernel-2s conv read through the
+        s-phase view has exactly this column order)."""
+        w = packing.fold_weight_norm(sd, prefix + ".conv")
+        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".conv.bias"])
+        self._tcw.append(W)
+        return W
+
+    def _tc_convtr(self, sd, prefix, stride):
+        w = packing.fold_weight_norm(sd, prefix + ".conv")  # [Cin, Cout, 2s]
+        p = packing.pack_convtr(w, stride)                  # [2, Cin, s*Cout]
+        W = TcWeights(p.permute(2, 0, 1).reshape(p.shape[2], -1), sd[prefix + ".conv.bias"].float().repeat(stride))
+        self._tcw.append(W)
+        return W
+
+    def _tc_resblock(self, sd, prefix):
+        k3 = self._tc_conv(sd, prefix + ".block.1")
+        wsc = packing.fold_weight_norm(sd, prefix + ".shortcut.conv")[:, :, 0]
+        w1 = packing.fold_weight_norm(sd, prefix + ".block.3.conv")[:, :, 0]
+        tail = TcWeights(torch.cat([wsc, w1], dim=1), sd[prefix + ".shortcut.conv.bias"] + sd[prefix + ".block.3.conv.bias"])
+        self._tcw.append(tail)
+        return k3, tail
+
+    def _tc_lstm(self, sd, prefix):
+        out = []
+        for l in range(2):
+            W = TcWeights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"])
+            self._tcw.append(W)
+            out.append(W)
+        return out
+
+    def _build_tc(self, sd):
+        if self.mode != "decode":
+            idx, self._tenc = 1, []
+            for r in reversed(RATIOS):
+                self._tenc.append((self._tc_resblock(sd, f"encoder.layers.{idx}"), self._tc_conv(sd, f"encoder.layers.{idx + 2}"), r))
+                idx += 3
+            self._tenc_lstm = self._tc_lstm(sd, f"encoder.layers.{idx}")
+            self._tenc_last = self._tc_conv(sd, f"encoder.layers.{idx + 2}")
+        if self.mode != "encode":
+            self._tdec_first = self._tc_conv(sd, "decoder.layers.0")
+            self._tdec_lstm = self._tc_lstm(sd, "decoder.layers.1")
+            idx, self._tdec = 3, []
+            for r in RATIOS:
+                self._tdec.append((self._tc_convtr(sd, f"decoder.layers.{idx}", r), self._tc_resblock(sd, f"decoder.layers.{idx + 1}"), r))
+                idx += 3
+
+    # ------------------------------------------------------------------ bf16 tensor-path execution
+    def _tc_run_lstm(self, Ws, whh, x: Act, final: Act):
+        """x raw [B,N,512] -> final = ELU(lstm(x) + x) (HF/encodec:236-249 + the following ELU)."""
+        B, N, C = x.B, x.L, x.C
+        dev = x.buf.device
+        pre = torch.empty((B, N, 4 * C), device=dev, dtype=torch.float32)
+        tc.conv_tc(Ws[0], [Src(x)], N, y32=pre, name="lstm_ih_tc")
+        h0 = Act(B, N, C, dev, split=True)
+        ops.lstm_layer_bf16(pre, getattr(self, whh[0]), self._sync_ws, out_bf16=h0)
+        tc.conv_tc(Ws[1], [Src(h0)], N, y32=pre, name="lstm_ih_tc")
+        ops.lstm_layer_bf16(pre, getattr(self, whh[1]), self._sync_ws, skip=x, final=final, final_act=ACT_ELU)
+
+    def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act):
+        """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe))))."""
+        B, L, C = x.B, x.L, x.C
+        xe.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
+        he = Act(B, L, C // 2, x.buf.device, split=C >= SPLIT_MIN_CH)
+        tc.conv_tc(Wk3, [Src(xe, taps=3, origin=-2, rows=L + 2)], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
+        tc.conv_tc(Wtail, [Src(x), Src(he)], L, y_act=ye, act=ACT_ELU, name="res_tail_tc")
+
+    def _encoder_tc(self, sig, vlen=None):
+        B, T = sig.shape
+        dev = sig.device
+        x = Act(B, T, 32, dev)
+        xe = Act(B, T, 32, dev, hl=2)
+        ops.conv(self._enc[0], sig.contiguous()[:, :, None], vlen=vlen, y_bf=x, y_act_bf=xe, act2=ACT_ELU, want_f32=False)
+        L = T
+        for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):
+            C = x.C
+            Lout = -(-L // r)
+            extra = Lout * r - L
+            ye = Act(B, L, C, dev, hl=r, hr=extra, split=C >= SPLIT_MIN_CH)
+            self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
+            ye.fill_halo(PAD_REFLECT, max(r, extra) + 1 if L <= max(r, extra) else 0)
+            last = i == len(self._tenc) - 1
+            x = Act(B, Lout, 2 * C, dev, split=2 * C >= SPLIT_MIN_CH)
+            xe = None if last else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= SPLIT_MIN_CH)
+            tc.conv_tc(Wdown, [Src(ye, taps=2, origin=-r, phases=r, rows=Lout + 1)], Lout, y=x, y_act=xe, act=ACT_ELU,
+                       name="down_tc")
+            L = Lout
+        le = Act(B, L, x.C, dev, hl=6, split=True)
+        self._tc_run_lstm(self._tenc_lstm, [n for _, n in self._enc_lstm], x, le)
+        le.fill_halo(PAD_REFLECT, 7 if L <= 6 else 0)
+        emb = torch.empty((B, L, 128), device=dev, dtype=torch.float32)
+        tc.conv_tc(self._tenc_last, [Src(le, taps=7, origin=-6, rows=L + 6)], L, y32=emb, name="conv_k7_tc")
+        return emb
+
+    def _decoder_tc(self, toks):
+        B, N, K = toks.shape
+        dev = toks.device
+        z = Act(B, N, 128, dev, hl=6, split=True)
+        ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks, K, z, err_flag=self._err)
+        z.fill_halo(PAD_REFLECT, 7 if N <= 6 else 0)
+        d0 = Act(B, N, 512, dev, split=True)
+        tc.conv_tc(self._tdec_first, [Src(z, taps=7, origin=-6, rows=N + 6)], N, y=d0, name="conv_k7_tc")
+        ye = Act(B, N, 512, dev, split=True)
+        self._tc_run_lstm(self._tdec_lstm, [n for _, n in self._dec_lstm], d0, ye)
+        L = N
+        for i, (Wtr, (Wk3, Wtail), r) in enumerate(self._tdec):
+            C = ye.C // 2
+            Lout = L * r
+            sp = C >= SPLIT_MIN_CH
+            x = Act(B, Lout, C, dev, split=sp)
+            xe = Act(B, Lout, C, dev, hl=2, split=sp)
+            # transposed conv: 2-tap GEMM over n = (phase, cout); row -1 reads as zero (TMA OOB fill)
+            tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C,
+                       name="convtr_tc")
+            ye = Act(B, Lout, C, dev, split=sp)
+            self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
+            L = Lout
+        # last layer Cout=1: SIMT kernel reading the (already ELU'd) bf16 activation, reflect padding by index math
+        sig = ops.conv(self._dec_last_noact, ye.data())
+        return sig[:, :, 0]
 
     # ------------------------------------------------------------------ pieces
     def _num_quantizers(self):
@@ -162,14 +296,15 @@ class Encodec(Codec):
 
     def _sig_to_toks(self, sig, length):
         nq = self._num_quantizers()
-        emb = self._encoder(sig, self._vlen(sig, length))
+        enc = self._encoder_tc if self.precision == "bf16" else self._encoder
+        emb = enc(sig, self._vlen(sig, length))
         B, N, D = emb.shape
         toks = torch.empty((B, N, nq), device=sig.device, dtype=torch.int64)
         ops.rvq_encode(emb.view(B * N, D), self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
         return toks  # [B, N, K]
 
     def _sig_to_feats(self, sig, length):  # R/audiocodecs/encodec.py:97-117 (normalize=False: mask unused)
-        return self._encoder(sig)
+        return (self._encoder_tc if self.precision == "bf16" else self._encoder)(sig)
 
     def _sig_to_qfeats(self, sig, length):  # R/audiocodecs/encodec.py:120-127
         return self._toks_to_qfeats(self._sig_to_toks(sig, length), length)
@@ -181,4 +316,6 @@ class Encodec(Codec):
         return q.view(B, N, -1)
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/encodec.py:130-141
+        if self.precision == "bf16":
+            return self._decoder_tc(toks.to(torch.int64).contiguous())
         return self._decoder(self._toks_to_qfeats(toks, length))

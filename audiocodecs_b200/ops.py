@@ -101,23 +101,33 @@ class ConvSpec:
 
 
 def conv(spec: ConvSpec, x: torch.Tensor, res: torch.Tensor = None, out: torch.Tensor = None,
-         vlen: torch.Tensor = None) -> torch.Tensor:
-    """x [B, L, Cin] -> y [B, Lout, Cout] (+res). `res` may alias `out`."""
+         vlen: torch.Tensor = None, y_bf=None, y_act_bf=None, act2=ACT_NONE, want_f32=True) -> torch.Tensor:
+    """x [B, L, Cin] (fp32, or the bf16 valid-row view of a tc.Act) -> y [B, Lout, Cout] (+res). `res` may alias
+    `out`.  y_bf / y_act_bf: optional tc.Act outputs (bf16 copy, bf16 act2(copy)) for the bf16 pipeline's edges."""
     _need_cuda(x, spec.w, res, out)
-    assert x.dtype == torch.float32 and x.dim() == 3 and x.stride(2) == 1 and x.shape[2] == spec.cin, (x.shape, spec.cin)
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 3 and x.stride(2) == 1 and x.shape[2] == spec.cin, (x.shape, spec.cin)
     B, L, _ = x.shape
     Lout = spec.out_len(L)
     if Lout <= 0:
         raise ValueError(f"input too short for this layer (L={L})")
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((B, Lout, spec.cout), device=x.device, dtype=torch.float32)
-    assert out.is_contiguous() and tuple(out.shape) == (B, Lout, spec.cout)
+    assert out is None or (out.is_contiguous() and tuple(out.shape) == (B, Lout, spec.cout))
     p = AcConvF32()
     p.x, p.w, p.bias, p.alpha = x.data_ptr(), spec.w.data_ptr(), _ptr(spec.bias), _ptr(spec.alpha)
-    p.res, p.y, p.vlen = _ptr(res), out.data_ptr(), _ptr(vlen)
+    p.res, p.y, p.vlen = _ptr(res), _ptr(out), _ptr(vlen)
+    p.x_is_bf16 = int(x.dtype == torch.bfloat16)
+    p.act2 = act2
+    for o in (y_bf, y_act_bf):
+        assert o is None or (o.L == Lout and o.C == spec.cout and o.B == B)
+    if y_bf is not None:
+        p.y_bf16, p.y_bf16_bstride = y_bf.row_ptr(0), y_bf.bstride
+    if y_act_bf is not None:
+        p.y_act_bf16, p.y_act_bstride = y_act_bf.row_ptr(0), y_act_bf.bstride
     if res is not None:
         assert res.shape == out.shape and res.is_contiguous()
-    p.x_bstride, p.y_bstride, p.res_bstride = x.stride(0), out.stride(0), (res.stride(0) if res is not None else 0)
+    p.x_bstride, p.y_bstride = x.stride(0), (out.stride(0) if out is not None else 0)
+    p.res_bstride = res.stride(0) if res is not None else 0
     p.x_rstride = x.stride(1)
     p.batch, p.x_rows, p.cin, p.n_cols, p.taps = B, L, spec.cin, spec.n_cols, spec.taps
     p.act, p.epi, p.pad_mode = spec.act, spec.epi, spec.pad_mode
@@ -144,7 +154,8 @@ def conv(spec: ConvSpec, x: torch.Tensor, res: torch.Tensor = None, out: torch.T
     if _PROFILER:
         # algorithmic work: 2 FLOP per MAC of the reference's dense op; fp32 activation bytes in+out
         _PROFILER.end("conv1d_f32", t0, 2.0 * B * p.m_rows * spec.n_cols * spec.taps * spec.cin,
-                      4.0 * (x.numel() + out.numel() + spec.w.numel()))
+                      float(x.element_size() * x.numel() + 4 * spec.w.numel() + B * Lout * spec.cout *
+                            (4 * (out is not None) + 2 * (y_bf is not None) + 2 * (y_act_bf is not None))))
     return out
 
 
@@ -161,6 +172,46 @@ def lstm_layer(pre, w_hh, skip, sync_ws):
     if _PROFILER:
         _PROFILER.end("lstm_layer_f32", t0, 2.0 * B * T * 4 * C * C, 4.0 * (pre.numel() + out.numel()))
     return out
+
+
+def lstm_layer_bf16(pre, w_hh, sync_ws, out_bf16=None, skip=None, final=None, final_act=ACT_NONE):
+    """bf16-pipeline LSTM layer: pre [B,T,4C] fp32 -> h; optional bf16 copy of h, and final = act(h + skip)
+    written into a tc.Act (skip: tc.Act)."""
+    from ._lib import AcLstmDesc
+    _need_cuda(pre, w_hh)
+    B, T, C4 = pre.shape
+    C = C4 // 4
+    out = torch.empty((B, T, C), device=pre.device, dtype=torch.float32)
+    d = AcLstmDesc()
+    d.pre, d.w_hh, d.out = pre.data_ptr(), w_hh.data_ptr(), out.data_ptr()
+    if out_bf16 is not None:  # tc.Act without halo
+        d.out_bf16 = out_bf16.row_ptr(0)
+        d.out_lo = out_bf16.lo_ptr(0)
+    if skip is not None:
+        d.skip_bf16, d.skip_bstride, d.skip_lo = skip.row_ptr(0), skip.bstride, skip.lo_ptr(0)
+    if final is not None:
+        d.final_bf16, d.final_bstride, d.final_lo = final.row_ptr(0), final.bstride, final.lo_ptr(0)
+    d.final_act, d.batch, d.steps, d.hidden, d.sync_ws = final_act, B, T, C, sync_ws.data_ptr()
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_lstm_layer(ctypes.byref(d), _stream()), "ac_lstm_layer")
+    if _PROFILER:
+        _PROFILER.end("lstm_layer_f32", t0, 2.0 * B * T * 4 * C * C, 4.0 * (pre.numel() + out.numel()))
+    return out
+
+
+def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=None):
+    """codes [B*N, Ktot] int64 -> bf16 rows of the tc.Act `out_act` ([B][hl+N+hr][D])."""
+    _need_cuda(codes, codebooks)
+    rows = codes.shape[0]
+    D = codebooks.shape[2]
+    assert codes.dtype == torch.int64 and codes.is_contiguous() and out_act.C == D and rows == out_act.B * out_act.L
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_rvq_decode_bf16(_ptr(codes), _ptr(codebooks), ctypes.c_void_p(out_act.row_ptr(0)),
+                                             ctypes.c_void_p(out_act.lo_ptr(0)) if out_act.lo is not None else None, rows, out_act.L,
+                                             out_act.bstride, D, codebooks.shape[1], stages, codes.shape[-1], code_offset,
+                                             _ptr(err_flag), _stream()), "ac_rvq_decode_bf16")
+    if _PROFILER:
+        _PROFILER.end("rvq_decode", t0, 0.0, 8.0 * rows * stages + 4.0 * rows * D * stages + 2.0 * rows * D)
 
 
 def rvq_encode(x, codebooks, cb_norm, codes_out, stages, code_offset=0, metric=0, residual_out=None):

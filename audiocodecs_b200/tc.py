@@ -1,0 +1,147 @@
+"""Host side of the bf16 tensor-core pipeline: haloed channels-last activation buffers, packed bf16
+weights and the launch helper around `ac_conv_tc` (include/audiocodecs_b200.h).
+
+Layout in HBM: every activation is `[B][halo_l + L + halo_r][C]` bf16.  Consumers never copy or pad:
+a conv reads its taps through a TMA view of the producer's buffer (view origin = first halo row it
+needs), a stride-s conv reads rows of s*C values of the same memory, a transposed conv writes the
+`[L*s][C]` tensor as the flat image of its `[L][s*C]` GEMM output.  Reflect halos (EnCodec) are a few
+rows written in place by `ac_pad_halo_bf16`; zero padding is TMA out-of-bounds fill.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from ._lib import AcConvTcDesc
+
+
+class Act:
+    """channels-last bf16 activation with halo rows."""
+
+    __slots__ = ("buf", "lo", "hl", "hr", "L", "C")
+
+    def __init__(self, B, L, C, device, hl=0, hr=0, zero=False, split=False):
+        """split=True adds a lo plane (x - bf16(x), also bf16): the pair carries ~16 mantissa bits through
+        the bf16 tensor cores (A_hi*W + A_lo*W_hi)."""
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc((B, hl + L + hr, C), device=device, dtype=torch.bfloat16)
+        self.lo = alloc((B, hl + L + hr, C), device=device, dtype=torch.bfloat16) if split else None
+        self.hl, self.hr, self.L, self.C = hl, hr, L, C
+
+    @property
+    def B(self):
+        return self.buf.shape[0]
+
+    @property
+    def bstride(self):
+        return self.buf.stride(0)
+
+    def row_ptr(self, row=0):
+        """address of valid row `row` (may be negative: halo) of clip 0"""
+        return self.buf.data_ptr() + (self.hl + row) * self.C * 2
+
+    def lo_ptr(self, row=0):
+        return None if self.lo is None else self.lo.data_ptr() + (self.hl + row) * self.C * 2
+
+    def data(self):
+        return self.buf[:, self.hl:self.hl + self.L]
+
+    def fill_halo(self, mode, reflect_len=0):
+        if self.hl + self.hr == 0:
+            return
+        t0 = ops._PROFILER.begin() if ops._PROFILER else None
+        for ptr in (self.row_ptr(0), self.lo_ptr(0)):
+            if ptr is not None:
+                _lib.check(_lib.lib().ac_pad_halo_bf16(ctypes.c_void_p(ptr), self.B, self.L, self.C, self.bstride, self.hl,
+                                                       self.hr, mode, max(reflect_len, self.L), ops._stream()), "ac_pad_halo_bf16")
+        if ops._PROFILER:
+            ops._PROFILER.end("pad_halo_bf16", t0, 0.0, 4.0 * self.B * (self.hl + self.hr) * self.C)
+
+
+class Src:
+    """one A source of the tap-GEMM: a view of an Act."""
+
+    __slots__ = ("act", "origin", "phases", "rows", "taps", "dilation", "shift")
+
+    def __init__(self, act, taps=1, dilation=1, shift=0, origin=0, phases=1, rows=None):
+        self.act, self.taps, self.dilation, self.shift = act, taps, dilation, shift
+        self.origin, self.phases = origin, phases
+        self.rows = rows if rows is not None else act.L
+
+
+def pick_bk(*channels):
+    for bk in (64, 32, 16):
+        if all(c % bk == 0 for c in channels):
+            return bk
+    raise ValueError(f"tensor path needs channel counts that are multiples of 16, got {channels}")
+
+
+class TcWeights:
+    """bf16 [n_total][k_total] + fp32 bias; `apply` supports module.to()."""
+
+    def __init__(self, w, bias, alpha=None, split=True):
+        """split: store W as the pair (W_hi, W_lo = bf16(W - W_hi)), stacked [2][n][k]; both tiles sit in shared memory
+        and every A tile is multiplied by both, so weight rounding error drops from 2^-9 to ~2^-17 at no HBM cost."""
+        w = w.float()
+        hi = w.to(torch.bfloat16)
+        self.split = bool(split)
+        self.w = (torch.stack([hi, (w - hi.float()).to(torch.bfloat16)]) if split else hi).contiguous()
+        self.bias = bias.float().contiguous() if bias is not None else None
+        self.alpha = alpha.float().contiguous() if alpha is not None else None
+        self.n_total, self.k_total = w.shape
+
+    def apply(self, fn):
+        self.w = fn(self.w)
+        self.bias = fn(self.bias) if self.bias is not None else None
+        self.alpha = fn(self.alpha) if self.alpha is not None else None
+
+
+def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32: torch.Tensor = None, res: Act = None,
+            act=ops.ACT_NONE, epi=ops.EPI_NONE, alpha=None, act_mod=0, out_rows=None, out_ch=None, out_shift=0, bk=None,
+            n_tile_hint=0, grid_hint=0, name="conv_tc"):
+    """Launch one tap-GEMM.  Outputs are Acts (bf16, flat layout starting at their valid row 0) and/or a
+    contiguous fp32 tensor [B, out_rows, out_ch]."""
+    d = AcConvTcDesc()
+    B = srcs[0].act.B
+    n = 0
+    for s in srcs:
+        a = s.act
+        hi_index = n
+        for base, lo_of in ((a.row_ptr(s.origin), -1), (a.lo_ptr(s.origin), hi_index)):
+            if base is None:
+                continue
+            S = d.src[n]
+            c0 = a.C
+            S.base = base
+            S.c0, S.phases, S.rows = c0, s.phases, s.rows
+            S.phase_stride, S.row_stride, S.batch_stride = c0, c0 * s.phases, a.bstride
+            S.taps, S.dilation, S.shift, S.lo_of = s.taps, s.dilation, s.shift, lo_of
+            n += 1
+    d.n_src = n
+    d.w, d.k_total, d.n_total, d.w_split = W.w.data_ptr(), W.k_total, W.n_total, int(W.split)
+    d.bk = bk or pick_bk(*[s.act.C for s in srcs])
+    d.bias = W.bias.data_ptr() if W.bias is not None else None
+    d.alpha = alpha.data_ptr() if alpha is not None else None
+    out_ch = out_ch or W.n_total
+    out_rows = out_rows or m_rows
+    d.out_shift, d.out_valid = out_shift, out_rows * out_ch
+    for o in (y, y_act, res):
+        if o is not None:
+            assert o.C == out_ch and o.L == out_rows and o.B == B, (o.C, out_ch, o.L, out_rows)
+    if y is not None:
+        d.y, d.y_bstride, d.y_lo = y.row_ptr(0), y.bstride, y.lo_ptr(0)
+    if y_act is not None:
+        d.y_act, d.y_act_bstride, d.y_act_lo = y_act.row_ptr(0), y_act.bstride, y_act.lo_ptr(0)
+    if res is not None:
+        d.res, d.res_bstride = res.row_ptr(0), res.bstride
+    if y32 is not None:
+        assert y32.is_contiguous() and y32.dtype == torch.float32 and y32.shape[0] == B and y32[0].numel() == out_rows * out_ch
+        d.y32, d.y32_bstride = y32.data_ptr(), y32.stride(0)
+    d.act, d.epi, d.act_mod = act, epi, act_mod or out_ch
+    d.batch, d.m_rows, d.n_tile_hint, d.grid_hint = B, m_rows, n_tile_hint, grid_hint
+    t0 = ops._PROFILER.begin() if ops._PROFILER else None
+    _lib.check(_lib.lib().ac_conv_tc(ctypes.byref(d), ops._stream()), "ac_conv_tc")
+    if ops._PROFILER:
+        n_out = sum(o is not None for o in (y, y_act)) * 2 + (4 if y32 is not None else 0) + (2 if res is not None else 0)
+        by = sum(2.0 * B * s.rows * s.phases * s.act.C for s in srcs) + n_out * B * out_rows * out_ch + 2.0 * W.w.numel()
+        ops._PROFILER.end(name, t0, 2.0 * B * m_rows * W.n_total * W.k_total, by)

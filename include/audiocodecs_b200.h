@@ -58,18 +58,24 @@ extern "C" {
  *           and every 1x1 projection / nn.Linear on the path.
  */
 typedef struct ac_conv_f32 {
-    const float* x;       /* [B][x_rows][cin] , clip stride x_bstride, row stride x_rstride */
+    const void* x;        /* [B][x_rows][cin] fp32 (or bf16 when x_is_bf16), clip stride x_bstride, row stride x_rstride */
     const float* w;       /* [taps][cin][n_cols] */
     const float* bias;    /* [n_cols] or NULL */
     const float* alpha;   /* [cin] snake alpha or NULL */
     const float* res;     /* residual, same flat layout as y, or NULL (may alias y) */
-    float* y;
+    float* y;             /* fp32 output or NULL */
     const int32_t* vlen;  /* optional [B]: input rows >= vlen[b] read as 0 (padding mask, HF/encodec:599-601) */
     int64_t x_bstride, y_bstride, res_bstride; /* elements */
     int32_t x_rstride;
     int32_t batch, x_rows, cin, m_rows, n_cols, taps, stride, dilation, pad_left;
     int32_t pad_mode, reflect_len, act, epi;
     int64_t out_shift, out_valid;
+    /* mixed-precision edges of the bf16 pipeline (first layer: fp32 waveform in, last layer: fp32 waveform out) */
+    int32_t x_is_bf16;
+    int32_t act2;         /* activation of the y_act_bf16 copy (AC_ACT_NONE / AC_ACT_ELU) */
+    void* y_bf16;         /* optional bf16 copy of the output, same flat layout */
+    void* y_act_bf16;     /* optional bf16 act2(output) */
+    int64_t y_bf16_bstride, y_act_bstride;
 } ac_conv_f32;
 
 AC_API int ac_conv1d_f32(const ac_conv_f32* p, void* stream);
@@ -83,6 +89,22 @@ AC_API int ac_conv1d_f32(const ac_conv_f32* p, void* stream);
  */
 AC_API int ac_lstm_layer_f32(const float* pre, const float* w_hh, const float* skip, float* out,
                       int32_t batch, int32_t steps, int32_t hidden, int32_t* sync_ws, void* stream);
+
+/* Same layer with the bf16 pipeline's edges: optional bf16 copy of h (input of the next layer's W_ih GEMM),
+ * bf16 skip input, and a bf16 output final[b][t][C] = act(h + skip) (clip stride final_bstride elements)
+ * which is what the consumer conv reads.  `out` (fp32 [B][T][C]) is always written: it carries h[t-1]. */
+typedef struct ac_lstm_desc {
+    const float* pre; const float* w_hh; float* out;
+    void* out_bf16;            /* bf16 [B][T][C] or NULL */
+    const void* skip_bf16;     /* bf16 [B][T][C] (clip stride skip_bstride) or NULL */
+    void* final_bf16;          /* bf16 act(h + skip) or NULL */
+    int64_t skip_bstride, final_bstride;
+    int32_t final_act;         /* AC_ACT_NONE / AC_ACT_ELU */
+    int32_t batch, steps, hidden;
+    int32_t* sync_ws;
+    void* out_lo; const void* skip_lo; void* final_lo; /* optional lo planes (x - bf16(x)) of out_bf16 / skip_bf16 / final_bf16 */
+} ac_lstm_desc;
+AC_API int ac_lstm_layer(const ac_lstm_desc* d, void* stream);
 
 /*
  * Residual VQ encode, all stages fused (fp32): for k < stages: idx = argmin_c ||r - E_k[c]||^2
@@ -105,6 +127,11 @@ AC_API int ac_rvq_encode_f32(const float* x, const float* codebooks, const float
 AC_API int ac_rvq_decode_f32(const int64_t* codes, const float* codebooks, float* out, int64_t rows, int32_t dim,
                       int32_t n_codes, int32_t stages, int32_t code_stride, int32_t code_offset,
                       int32_t* err_flag, void* stream);
+/* same sum, also/only written as bf16 into a haloed activation buffer: row r of clip b at
+ * out_bf16[b*bstride + r*dim] (rows_per_clip rows per clip). */
+AC_API int ac_rvq_decode_bf16(const int64_t* codes, const float* codebooks, void* out_bf16, void* out_lo, int64_t rows,
+                      int32_t rows_per_clip, int64_t bstride, int32_t dim, int32_t n_codes, int32_t stages,
+                      int32_t code_stride, int32_t code_offset, int32_t* err_flag, void* stream);
 
 /*
  * Polyphase windowed-sinc resampler (torchaudio.functional.resample, TA:1405-1432):
@@ -114,6 +141,65 @@ AC_API int ac_rvq_decode_f32(const int64_t* codes, const float* codebooks, float
 AC_API int ac_resample_f32(const float* x, const float* taps, float* y, int32_t batch, int64_t in_len,
                     int64_t out_len, int32_t orig, int32_t n_phase, int32_t n_taps, int32_t width,
                     void* stream);
+
+
+/*
+ * bf16 tensor-core tap-GEMM convolution (tcgen05.mma + TMEM accumulators, operands staged by TMA):
+ *
+ *   acc[b][m][n] = bias[n] + sum_{s<n_src} sum_{j<taps_s} sum_{k<c0_s*phases_s}
+ *                      A_s[b][m + j*dilation_s + shift_s][k] * W[n][col(s,j,k)]
+ *   flat = m*n_total + n - out_shift ; if 0 <= flat < out_valid:
+ *       v = epi(acc) (+ res[b][flat]);  y[b][flat] = bf16(v);  y32[b][flat] = v;  y_act[b][flat] = bf16(act(v))
+ *
+ * A_s is a VIEW of a channels-last bf16 activation buffer: view row = `phases` consecutive time steps
+ * of `c0` channels, so a stride-s / kernel-2s convolution is a 2-tap GEMM over rows of s*c0 values and
+ * a transposed convolution is a 2-tap GEMM whose n axis is (phase, cout).  Rows outside [0, rows) read
+ * as zero (TMA out-of-bounds fill) -- zero padding costs nothing; reflect padding is materialised by the
+ * producer in the buffer's halo rows (ac_pad_halo_bf16).  Two sources let one GEMM take its taps from two
+ * tensors (EnCodec ResBlock: shortcut(x) + conv_k1(ELU(h)) is one launch).  `y_act` receives the
+ * activation the CONSUMER layer applies (ELU / Snake with the consumer's alpha), so activations are
+ * applied once, at production time.  W is bf16 [n_total][k_total], columns ordered source, tap, k.
+ * Replaces the same reference code as ac_conv1d_f32 (HF/encodec:82-282, HF/mimi:214-451, HF/dac:173-262,405-472).
+ */
+typedef struct ac_tc_src {
+    const void* base;            /* bf16: view row 0, phase 0, channel 0 of clip 0 */
+    int32_t c0, phases, rows;    /* channels per phase, phases per view row, view rows per clip */
+    int64_t phase_stride, row_stride, batch_stride; /* elements */
+    int32_t taps, dilation, shift; /* tap j reads view row m + j*dilation + shift */
+    int32_t lo_of;               /* -1, or index of the source whose lo plane (x - bf16(x)) this is: it re-uses that
+                                    source's weight columns (split-bf16 activations, fp32-accurate products) */
+} ac_tc_src;
+
+typedef struct ac_conv_tc_desc {
+    ac_tc_src src[4];
+    int32_t n_src;
+    const void* w;               /* bf16 [n_total][k_total]; with w_split: [2][n_total][k_total] = W_hi then W_lo = bf16(W - W_hi) */
+    int32_t w_split;             /* 1: every product also accumulates A*W_lo (error-compensated weights, no HBM cost) */
+    int32_t k_total, n_total, bk; /* bk: contraction block 16/32/64, must divide every source's c0 */
+    const float* bias;           /* [n_total] or NULL */
+    const float* alpha;          /* snake alpha of the consumer, [act_mod] */
+    const void* res;             /* bf16 residual in the output's flat layout, or NULL */
+    void* y;                     /* bf16 out or NULL */
+    void* y_act;                 /* bf16 act(out) or NULL */
+    void* y_lo;                  /* optional lo planes of y / y_act (same strides): bf16(v - float(bf16(v))) */
+    void* y_act_lo;
+    float* y32;                  /* fp32 out or NULL */
+    int32_t act, epi, act_mod;   /* act: AC_ACT_* for y_act; epi: AC_EPI_*; channel of column n = n % act_mod */
+    int64_t y_bstride, y_act_bstride, y32_bstride, res_bstride; /* elements per clip */
+    int64_t out_shift, out_valid;
+    int32_t batch, m_rows;
+    int32_t n_tile_hint, grid_hint; /* 0 = automatic */
+} ac_conv_tc_desc;
+
+AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
+
+/*
+ * Fill the halo rows of a channels-last bf16 activation buffer [batch][halo_l + rows + halo_r][ch] from its
+ * valid rows: mode AC_PAD_REFLECT (EnCodec, incl. the zero-extension rule for tiny inputs via reflect_len),
+ * AC_PAD_REPLICATE (Mimi downsample) or AC_PAD_ZERO.  `data` points at valid row 0 of clip 0.
+ */
+AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
+                            int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream);
 
 AC_API int ac_abi_version(void);
 AC_API const char* ac_last_error(void);

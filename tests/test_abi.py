@@ -19,8 +19,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_mirror_matches_header_size():
-    # 7 pointers + 3 int64 + 14 int32 + 2 int64, natural alignment
-    assert ctypes.sizeof(_lib.AcConvF32) == 7 * 8 + 3 * 8 + 14 * 4 + 2 * 8
+    # 7 pointers + 3 int64 + 14 int32 + 2 int64 + 2 int32 + 2 pointers + 2 int64, natural alignment
+    assert ctypes.sizeof(_lib.AcConvF32) == 7 * 8 + 3 * 8 + 14 * 4 + 2 * 8 + 2 * 4 + 2 * 8 + 2 * 8
+    assert ctypes.sizeof(_lib.AcTcSrc) == 8 + 3 * 4 + 4 + 3 * 8 + 4 * 4
+
 
 
 def test_no_cpu_fallback(encodec_sd):

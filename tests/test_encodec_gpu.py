@@ -16,6 +16,7 @@ def dev():
 
 def _codec(sd, dev, **kw):
     import audiocodecs_b200 as A
+    kw.setdefault("precision", "fp32")  # exact-parity path; the bf16 tensor path is tested in test_encodec_bf16_gpu.py
     return A.Encodec(kw.pop("sample_rate", 24000), 24000, state_dict=sd, **kw).eval().to(dev)
 
 
