@@ -55,6 +55,13 @@ class AcLstmDesc(ctypes.Structure):
                 ("out_lo", c_vp), ("skip_lo", c_vp), ("final_lo", c_vp)]
 
 
+class AcLstmTcDesc(ctypes.Structure):
+    """mirror of `struct ac_lstm_tc_desc`"""
+    _fields_ = [("pre", c_vp), ("w_hh_bf16", c_vp), ("out_hi", c_vp), ("out_lo", c_vp), ("skip_hi", c_vp), ("skip_lo", c_vp),
+                ("final_hi", c_vp), ("final_lo", c_vp), ("skip_bstride", c_i64), ("final_bstride", c_i64),
+                ("final_act", c_i32), ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32)]
+
+
 def declared_symbols():
     """Every `AC_API` entry point the public header declares."""
     with open(HEADER_PATH) as f:
@@ -83,6 +90,7 @@ def lib():
         L.ac_rvq_encode_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_rvq_decode_f32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_resample_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_lstm_tc.argtypes = [ctypes.POINTER(AcLstmTcDesc), c_vp]
         L.ac_lstm_layer.argtypes = [ctypes.POINTER(AcLstmDesc), c_vp]
         L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]

@@ -263,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }

@@ -81,6 +81,9 @@ class Encodec(Codec):
             self._specs.append(spec)
             self.register_buffer(f"{name}_whh{l}", sd[f"{prefix}.lstm.weight_hh_l{l}"].float().contiguous(),
                                  persistent=False)
+            if self.precision == "bf16":
+                self.register_buffer(f"{name}_whh{l}_bf16", sd[f"{prefix}.lstm.weight_hh_l{l}"].to(torch.bfloat16).contiguous(),
+                                     persistent=False)
             layers.append((spec, f"{name}_whh{l}"))
         return layers
 
@@ -180,9 +183,9 @@ class Encodec(Codec):
         pre = torch.empty((B, N, 4 * C), device=dev, dtype=torch.float32)
         tc.conv_tc(Ws[0], [Src(x)], N, y32=pre, name="lstm_ih_tc")
         h0 = Act(B, N, C, dev, split=True)
-        ops.lstm_layer_bf16(pre, getattr(self, whh[0]), self._sync_ws, out_bf16=h0)
+        ops.lstm_tc(pre, getattr(self, whh[0] + "_bf16"), out=h0)
         tc.conv_tc(Ws[1], [Src(h0)], N, y32=pre, name="lstm_ih_tc")
-        ops.lstm_layer_bf16(pre, getattr(self, whh[1]), self._sync_ws, skip=x, final=final, final_act=ACT_ELU)
+        ops.lstm_tc(pre, getattr(self, whh[1] + "_bf16"), skip=x, final=final, final_act=ACT_ELU)
 
     def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act):
         """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe))))."""

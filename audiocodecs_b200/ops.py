@@ -199,6 +199,27 @@ def lstm_layer_bf16(pre, w_hh, sync_ws, out_bf16=None, skip=None, final=None, fi
     return out
 
 
+def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE):
+    """tensor-core LSTM recurrence: pre [B,T,2048] fp32; out / skip / final are tc.Act (bf16 hi[/lo] planes)."""
+    from ._lib import AcLstmTcDesc
+    _need_cuda(pre, w_hh_bf16)
+    B, T, C4 = pre.shape
+    d = AcLstmTcDesc()
+    d.pre, d.w_hh_bf16 = pre.data_ptr(), w_hh_bf16.data_ptr()
+    if out is not None:
+        assert out.hl == 0 and out.hr == 0
+        d.out_hi, d.out_lo = out.row_ptr(0), out.lo_ptr(0)
+    if skip is not None:
+        d.skip_hi, d.skip_lo, d.skip_bstride = skip.row_ptr(0), skip.lo_ptr(0), skip.bstride
+    if final is not None:
+        d.final_hi, d.final_lo, d.final_bstride = final.row_ptr(0), final.lo_ptr(0), final.bstride
+    d.final_act, d.batch, d.steps, d.hidden = final_act, B, T, C4 // 4
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
+    if _PROFILER:
+        _PROFILER.end("lstm_tc", t0, 2.0 * B * T * C4 * (C4 // 4), 4.0 * pre.numel() + 2.0 * B * T * (C4 // 4))
+
+
 def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=None):
     """codes [B*N, Ktot] int64 -> bf16 rows of the tc.Act `out_act` ([B][hl+N+hr][D])."""
     _need_cuda(codes, codebooks)

@@ -107,6 +107,24 @@ typedef struct ac_lstm_desc {
 AC_API int ac_lstm_layer(const ac_lstm_desc* d, void* stream);
 
 /*
+ * Tensor-core LSTM layer recurrence (hidden = 512): one cluster of 16 CTAs per 16 clips, W_hh (bf16) resident in
+ * shared memory, h exchanged through distributed shared memory, one tcgen05.mma chain per step (see csrc/lstm_tc.cu).
+ * pre [B][T][4*hidden] fp32 holds W_ih x + b_ih + b_hh (ac_conv_tc with y32).  Outputs: bf16 h planes (hi [+lo]) for
+ * the next layer's input GEMM, and/or final = act(h + skip) planes in a haloed activation buffer.
+ * Replaces EncodecLSTM (HF/encodec:236-249).
+ */
+typedef struct ac_lstm_tc_desc {
+    const float* pre;
+    const void* w_hh_bf16;     /* bf16 [4*hidden][hidden], gate order i,f,g,o */
+    void* out_hi; void* out_lo;             /* bf16 [B][T][hidden] or NULL */
+    const void* skip_hi; const void* skip_lo; /* bf16, clip stride skip_bstride */
+    void* final_hi; void* final_lo;         /* bf16, clip stride final_bstride */
+    int64_t skip_bstride, final_bstride;
+    int32_t final_act, batch, steps, hidden;
+} ac_lstm_tc_desc;
+AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
+
+/*
  * Residual VQ encode, all stages fused (fp32): for k < stages: idx = argmin_c ||r - E_k[c]||^2
  * (reference formula and tie rule: first index wins), r -= E_k[idx].
  *   metric 0: EnCodec  dist = -(|r|^2 - 2 r.E + |E|^2), argmax   (HF/encodec:364-369,424-438)

@@ -63,3 +63,38 @@ def test_end_to_end_code_match_report(encodec_sd, dev):
     assert per_stage[0] > 0.85 and min(per_stage) > 0.5
     rec = codec.toks_to_sig(toks)
     assert tuple(rec.shape) == (4, 48000) and torch.isfinite(rec).all()
+
+
+@pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12)])
+def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T):
+    """tcgen05 cluster LSTM (bf16 W_hh and h operands, fp32 accumulate / cell state) vs the oracle's explicit loop."""
+    from audiocodecs_b200 import ops
+    from audiocodecs_b200.tc import Act
+    g = torch.Generator().manual_seed(77)
+    C = 512
+    pre = torch.randn(B, T, 4 * C, generator=g)
+    w_hh = encodec_sd["encoder.layers.13.lstm.weight_hh_l0"]
+    skip = torch.randn(B, T, C, generator=g)
+    # oracle: explicit recurrence on the given pre-gates
+    h = torch.zeros(B, C); c = torch.zeros(B, C); outs = []
+    for t in range(T):
+        gates = pre[:, t] + h @ w_hh.t()
+        i, f, gg, o = gates.split(C, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    ref = torch.stack(outs, 1)
+    out = Act(B, T, C, dev, split=True)
+    sk = Act(B, T, C, dev, split=True)
+    sk.buf.copy_(skip.to(torch.bfloat16)); sk.lo.copy_((skip - skip.to(torch.bfloat16).float()).to(torch.bfloat16))
+    fin = Act(B, T, C, dev, hl=3, split=True)
+    ops.lstm_tc(pre.to(dev), w_hh.to(torch.bfloat16).to(dev), out=out, skip=sk, final=fin, final_act=ops.ACT_ELU)
+    torch.cuda.synchronize()
+    got = out.buf.float().cpu() + out.lo.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    print(f"lstm_tc max|err| {err:.2e} (B={B}, T={T})")
+    assert err < 2e-2, err
+    ref_fin = torch.nn.functional.elu(ref + skip)
+    got_fin = (fin.data().float() + fin.lo[:, 3:3 + T].float()).cpu()
+    assert (got_fin - ref_fin).abs().max().item() < 3e-2
