@@ -31,6 +31,14 @@ inline int finish_launch(const char* what) {
     } while (0)
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU for the tensor-path epilogues: exp via MUFU (+ a 5-term series near 0 where exp(x)-1 cancels); abs error < 3e-7,
+// far below the bf16 (2^-9) / split-bf16 (2^-17) rounding that follows.  expm1f costs ~4x more issue slots.
+__device__ __forceinline__ float elu_fast(float x) {
+    const float series = x * (1.0f + x * (0.5f + x * (0.16666667f + x * (0.041666668f + x * 0.0083333338f))));
+    const float big = __expf(x) - 1.0f;
+    const float neg = x > -0.0625f ? series : big;
+    return x > 0.f ? x : neg;
+}
 __device__ __forceinline__ float snake(float x, float a) {
     float s = sinf(a * x);
     return x + (1.0f / (a + 1e-9f)) * (s * s);

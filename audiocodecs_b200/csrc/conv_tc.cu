@@ -24,7 +24,8 @@ using namespace sm100;
 
 constexpr int TILE_M = 128;
 constexpr int MAX_STAGES = 8;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over 16-column chunks
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 constexpr int MAX_SRC = 4;
 
@@ -100,7 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         if (p.n_src > 3) prefetch_tensormap(&amap3);
         prefetch_tensormap(&bmap);
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -179,8 +180,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             }
         }
     } else {
-        // ================================================================= epilogue (warps 2..5)
+        // ================================================================= epilogue (warps 2..9)
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int chunk0 = (warp - 2) >> 2;  // this warp takes chunks chunk0, chunk0+2, ...
         const int row_in_tile = quarter * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -195,7 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
             const int m = mt * TILE_M + row_in_tile;
             const bool row_ok = m < p.m_rows;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.n_tile;
-            for (int c = 0; c < p.n_tile / 16; ++c) {
+            for (int c = chunk0; c < p.n_tile / 16; c += EPI_WARPS / 4) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c * 16, v);
                 tmem_ld_wait();
@@ -239,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
                         float a[8];
                         if (p.act == AC_ACT_ELU) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = ac::elu1(o[i]);
+                            for (int i = 0; i < 8; ++i) a[i] = ac::elu_fast(o[i]);
                         } else if (p.act == AC_ACT_SNAKE) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) a[i] = ac::snake(o[i], __ldg(p.alpha + (n0 + h * 8 + i) % p.act_mod));

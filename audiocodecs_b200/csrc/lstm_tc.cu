@@ -44,6 +44,7 @@ struct LstmTcParams {
     __nv_bfloat16* fin_lo;
     long long skip_bs, fin_bs;
     int fin_act, batch, steps;
+    long long* dbg;  // optional [steps][8] clock64 samples from cluster 0 / CTA 0 (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -97,6 +98,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
+template <int NBV>  // clips handled per cluster (8 or 16); the UMMA N stays 16, unused B rows are zero
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -114,7 +116,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int clip0 = cluster_id_x() * NB;
+    const int clip0 = cluster_id_x() * NBV;
 
     if (threadIdx.x == 0) {
         prefetch_tensormap(&wmap);
@@ -150,6 +152,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                 const int par = t & 1;
                 if (t > 0) mbar_wait_cluster(&h_ready[par], ((t - 1) >> 1) & 1);  // h[t-1] complete in buffer `par`
                 tc_fence_after();
+                if (p.dbg && blockIdx.x == 0) { p.dbg[t * 8 + 5] = clock64(); }
                 const uint32_t a0 = smem_u32(a_s), b0 = smem_u32(b_s + par * B_BYTES);
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
@@ -159,93 +162,115 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                     for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
                 }
                 umma_commit(d_full);
+                if (p.dbg && blockIdx.x == 0) { p.dbg[t * 8 + 6] = clock64(); }
             }
         }
     } else {
         // ======================================================== epilogue: 128 threads
+        constexpr int CPT = NBV / 4;       // clips per thread in the cell update
+        constexpr int GROUPS = 128 / (NBV * 4);  // thread groups sharing the 16 destination CTAs of the broadcast
+        constexpr int DPT = CL / GROUPS;   // destinations per thread
         const int e = threadIdx.x - 64;
         const int g = warp & 3;            // TMEM lane quarter == gate index (rows g*32 + u)
         const int u = lane;
-        const int bq = e >> 5;             // clip quad for the cell update: clips 4bq..4bq+3
+        const int bq = e >> 5;             // clips bq*CPT .. for the cell update
         const int gu = (int)rank * UPC + u;
-        float c_state[4] = {0.f, 0.f, 0.f, 0.f};
-        float pre_next[NB];
+        float c_state[CPT], h_prev[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) { c_state[i] = 0.f; h_prev[i] = 0.f; }
+        float pre_next[NBV];
         auto load_pre = [&](int t) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
+            for (int b = 0; b < NBV; ++b) {
                 const int clip = clip0 + b;
                 pre_next[b] = clip < p.batch ? __ldg(p.pre + ((size_t)clip * p.steps + t) * (4 * HID) + g * HID + gu) : 0.f;
             }
         };
+        // global outputs of step t are written one step late, while this thread would otherwise idle on the MMA:
+        // keeping them off the path between the DSMEM stores and the cluster-scope release (which waits for
+        // every earlier store of the thread) is worth ~2000 cycles per step.
+        auto emit = [&](int t) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const int clip = clip0 + bq * CPT + i;
+                if (clip >= p.batch) continue;
+                const float h = h_prev[i];
+                const __nv_bfloat16 hb = __float2bfloat16(h);
+                const size_t o = ((size_t)clip * p.steps + t) * HID + gu;
+                if (p.out_hi) {
+                    p.out_hi[o] = hb;
+                    if (p.out_lo) p.out_lo[o] = __float2bfloat16(h - __bfloat162float(hb));
+                }
+                if (p.fin_hi) {
+                    float y = h;
+                    const size_t so = (size_t)clip * p.skip_bs + (size_t)t * HID + gu;
+                    if (p.skip_hi) y += __bfloat162float(p.skip_hi[so]);
+                    if (p.skip_lo) y += __bfloat162float(p.skip_lo[so]);
+                    if (p.fin_act == AC_ACT_ELU) y = elu_f(y);
+                    const __nv_bfloat16 yb = __float2bfloat16(y);
+                    const size_t fo = (size_t)clip * p.fin_bs + (size_t)t * HID + gu;
+                    p.fin_hi[fo] = yb;
+                    if (p.fin_lo) p.fin_lo[fo] = __float2bfloat16(y - __bfloat162float(yb));
+                }
+            }
+        };
         load_pre(0);
         for (int t = 0; t < p.steps; ++t) {
-            float pre_cur[NB];
+            float pre_cur[NBV];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) pre_cur[b] = pre_next[b];
+            for (int b = 0; b < NBV; ++b) pre_cur[b] = pre_next[b];
             if (t + 1 < p.steps) load_pre(t + 1);  // in flight during this step's MMA
+            if (t > 0) emit(t - 1);
+            const bool dbg = p.dbg && blockIdx.x == 0 && e == 0;
+            if (dbg) p.dbg[t * 8 + 0] = clock64();
             mbar_wait(d_full, t & 1);
             tc_fence_after();
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(g * 32) << 16), v);
+            if (dbg) p.dbg[t * 8 + 1] = clock64();
+            uint32_t v[NBV];
+            if constexpr (NBV == 16) tmem_ld16(tmem_d + ((uint32_t)(g * 32) << 16), v);
+            else tmem_ld8(tmem_d + ((uint32_t)(g * 32) << 16), v);
             tmem_ld_wait();
             tc_fence_before();
+            if (g == 2) {  // warp-uniform: the g gate is tanh, i/f/o are sigmoids
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float x = __uint_as_float(v[b]) + pre_cur[b];
-                gs[(g * UPC + u) * 17 + b] = (g == 2) ? fast_tanh(x) : fast_sigmoid(x);
+                for (int b = 0; b < NBV; ++b) gs[(g * UPC + u) * 17 + b] = fast_tanh(__uint_as_float(v[b]) + pre_cur[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < NBV; ++b) gs[(g * UPC + u) * 17 + b] = fast_sigmoid(__uint_as_float(v[b]) + pre_cur[b]);
             }
             epi_bar_sync();
-            // cell update for unit u, clips 4bq..4bq+3
+            if (dbg) p.dbg[t * 8 + 2] = clock64();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = bq * 4 + i;
+            for (int i = 0; i < CPT; ++i) {
+                const int b = bq * CPT + i;
                 const float ig = gs[(0 * UPC + u) * 17 + b], fg = gs[(1 * UPC + u) * 17 + b];
                 const float gg = gs[(2 * UPC + u) * 17 + b], og = gs[(3 * UPC + u) * 17 + b];
                 c_state[i] = fg * c_state[i] + ig * gg;
-                const float h = og * fast_tanh(c_state[i]);
-                const __nv_bfloat16 hb = __float2bfloat16(h);
-                hs[b * UPC + u] = hb;
-                const int clip = clip0 + b;
-                if (clip < p.batch) {
-                    const size_t o = ((size_t)clip * p.steps + t) * HID + gu;
-                    if (p.out_hi) {
-                        p.out_hi[o] = hb;
-                        if (p.out_lo) p.out_lo[o] = __float2bfloat16(h - __bfloat162float(hb));
-                    }
-                    if (p.fin_hi) {
-                        float y = h;
-                        const size_t so = (size_t)clip * p.skip_bs + (size_t)t * HID + gu;
-                        if (p.skip_hi) y += __bfloat162float(p.skip_hi[so]);
-                        if (p.skip_lo) y += __bfloat162float(p.skip_lo[so]);
-                        if (p.fin_act == AC_ACT_ELU) y = elu_f(y);
-                        const __nv_bfloat16 yb = __float2bfloat16(y);
-                        const size_t fo = (size_t)clip * p.fin_bs + (size_t)t * HID + gu;
-                        p.fin_hi[fo] = yb;
-                        if (p.fin_lo) p.fin_lo[fo] = __float2bfloat16(y - __bfloat162float(yb));
-                    }
-                }
+                h_prev[i] = og * fast_tanh(c_state[i]);
+                hs[b * UPC + u] = __float2bfloat16(h_prev[i]);
             }
+            if (dbg) p.dbg[t * 8 + 3] = clock64();
             if (t + 1 < p.steps) {
                 epi_bar_sync();  // hs complete (and gs reads finished)
                 // broadcast the slice into parity (t+1)&1 of every CTA's B operand, in its swizzled K-major position
                 const int npar = (t + 1) & 1;
-                const int b = e >> 3;            // clip row 0..15
-                const int jj = (e >> 1) & 3;     // 16-byte unit of the 64-byte slice row
+                const int b = e / (4 * GROUPS);      // clip row
+                const int jj = (e / GROUPS) & 3;     // 16-byte unit of the 64-byte slice row
+                const int grp = e % GROUPS;
                 const uint4 val = *reinterpret_cast<const uint4*>(hs + b * UPC + jj * 8);
                 const int kc = (int)rank >> 1;
                 const int unit = 4 * ((int)rank & 1) + jj;
                 const uint32_t off = (uint32_t)(npar * B_BYTES + kc * 2048 + b * 128 + ((unit ^ (b & 7)) << 4));
                 const uint32_t local = smem_u32(b_s) + off;
 #pragma unroll
-                for (int d = 0; d < 8; ++d) st_cluster_v4(map_to_cta(local, (uint32_t)((e & 1) * 8 + d)), val);
+                for (int d = 0; d < DPT; ++d) st_cluster_v4(map_to_cta(local, (uint32_t)(grp * DPT + d)), val);
                 fence_proxy_async_all();  // generic-proxy stores -> visible to the peers' async-proxy (tcgen05) reads
                 epi_bar_sync();
-                if (warp == 2 && lane < CL) {
-                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                    mbar_arrive_remote_release(map_to_cta(smem_u32(&h_ready[npar]), (uint32_t)lane));
-                }
+                if (dbg) p.dbg[t * 8 + 4] = clock64();
+                if (warp == 2 && lane < CL) mbar_arrive_remote_release(map_to_cta(smem_u32(&h_ready[npar]), (uint32_t)lane));
             }
         }
+        emit(p.steps - 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -288,11 +313,16 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
         AC_REQUIRE(r == CUDA_SUCCESS, "ac_lstm_tc: cuTensorMapEncodeTiled failed: %d", (int)r);
     }
     const size_t smem = 1024 + A_BYTES + 2 * B_BYTES + GS_FLOATS * 4 + NB * UPC * 2 + 64;
+    // Only 4 clusters of 16 CTAs are co-resident on a B200 (measured: 8 clusters ran as two waves), so a cluster
+    // takes 16 clips unless the whole batch fits in 4 clusters of 8 (half the per-step epilogue work).
+    const int nbv = d->batch <= 32 ? 8 : 16;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: func attributes: %s", cudaGetErrorString(e)); return (int)e; }
+        for (const void* fn : {(const void*)lstm_tc_kernel<8>, (const void*)lstm_tc_kernel<16>}) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: func attributes: %s", cudaGetErrorString(e)); return (int)e; }
+        }
         configured = true;
     }
     LstmTcParams p{};
@@ -302,8 +332,9 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     p.fin_hi = (__nv_bfloat16*)d->final_hi; p.fin_lo = (__nv_bfloat16*)d->final_lo;
     p.skip_bs = d->skip_bstride; p.fin_bs = d->final_bstride;
     p.fin_act = d->final_act; p.batch = d->batch; p.steps = d->steps;
+    p.dbg = (long long*)d->dbg;
 
-    const int clusters = (d->batch + NB - 1) / NB;
+    const int clusters = (d->batch + nbv - 1) / nbv;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CL);
     cfg.blockDim = dim3(THREADS);
@@ -316,7 +347,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_kernel, wmap, p);
+    cudaError_t e = nbv == 8 ? cudaLaunchKernelEx(&cfg, lstm_tc_kernel<8>, wmap, p) : cudaLaunchKernelEx(&cfg, lstm_tc_kernel<16>, wmap, p);
     ac::count_launch();
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

@@ -200,7 +200,7 @@ class Encodec(Codec):
         dev = sig.device
         x = Act(B, T, 32, dev)
         xe = Act(B, T, 32, dev, hl=2)
-        ops.conv(self._enc[0], sig.contiguous()[:, :, None], vlen=vlen, y_bf=x, y_act_bf=xe, act2=ACT_ELU, want_f32=False)
+        ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU, vlen=vlen)
         L = T
         for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):
             C = x.C
@@ -246,8 +246,7 @@ class Encodec(Codec):
             self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
             L = Lout
         # last layer Cout=1: SIMT kernel reading the (already ELU'd) bf16 activation, reflect padding by index math
-        sig = ops.conv(self._dec_last_noact, ye.data())
-        return sig[:, :, 0]
+        return ops.conv_last_bf16(self._dec_last, ye)
 
     # ------------------------------------------------------------------ pieces
     def _num_quantizers(self):

@@ -199,7 +199,42 @@ def lstm_layer_bf16(pre, w_hh, sync_ws, out_bf16=None, skip=None, final=None, fi
     return out
 
 
-def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE):
+def conv_first_bf16(spec, sig, y=None, y_act=None, act=ACT_NONE, vlen=None, pad_left=None, alpha=None):
+    """Cin=1 first layer of the bf16 pipeline: sig [B,T] fp32 -> tc.Act outputs (raw / activated)."""
+    _need_cuda(sig, spec.w)
+    B, T = sig.shape
+    sig = sig.contiguous()
+    K, C = spec.taps, spec.cout
+    if pad_left is None:
+        pad_left = (K - 1) if spec.geometry == "causal" else spec.padding
+    reflect_len = pad_left + 1 if (spec.pad_mode == PAD_REFLECT and T <= pad_left) else T
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_conv_first_bf16(
+        _ptr(sig), _ptr(spec.w), _ptr(spec.bias), _ptr(alpha), _ptr(vlen),
+        ctypes.c_void_p(y.row_ptr(0)) if y is not None else None, ctypes.c_void_p(y_act.row_ptr(0)) if y_act is not None else None,
+        y.bstride if y is not None else 0, y_act.bstride if y_act is not None else 0, B, T, C, K, pad_left, spec.pad_mode,
+        reflect_len, act, _stream()), "ac_conv_first_bf16")
+    if _PROFILER:
+        _PROFILER.end("conv_first", t0, 2.0 * B * T * K * C, 4.0 * B * T + 2.0 * B * T * C * ((y is not None) + (y_act is not None)))
+
+
+def conv_last_bf16(spec, x_act, epi=EPI_NONE, pad_left=None):
+    """Cout=1 last layer of the bf16 pipeline: tc.Act [B,T,C] (already activated) -> sig [B,T] fp32."""
+    _need_cuda(spec.w)
+    B, T, C, K = x_act.B, x_act.L, x_act.C, spec.taps
+    if pad_left is None:
+        pad_left = (K - 1) if spec.geometry == "causal" else spec.padding
+    reflect_len = pad_left + 1 if (spec.pad_mode == PAD_REFLECT and T <= pad_left) else T
+    out = torch.empty((B, T), device=x_act.buf.device, dtype=torch.float32)
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_conv_last_bf16(ctypes.c_void_p(x_act.row_ptr(0)), _ptr(spec.w), _ptr(spec.bias), _ptr(out), x_act.bstride,
+                                            B, T, C, K, pad_left, spec.pad_mode, reflect_len, epi, _stream()), "ac_conv_last_bf16")
+    if _PROFILER:
+        _PROFILER.end("conv_last", t0, 2.0 * B * T * K * C, 2.0 * B * T * C + 4.0 * B * T)
+    return out
+
+
+def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE, dbg=None):
     """tensor-core LSTM recurrence: pre [B,T,2048] fp32; out / skip / final are tc.Act (bf16 hi[/lo] planes)."""
     from ._lib import AcLstmTcDesc
     _need_cuda(pre, w_hh_bf16)
@@ -214,6 +249,7 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE)
     if final is not None:
         d.final_hi, d.final_lo, d.final_bstride = final.row_ptr(0), final.lo_ptr(0), final.bstride
     d.final_act, d.batch, d.steps, d.hidden = final_act, B, T, C4 // 4
+    d.dbg = _ptr(dbg)
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
     if _PROFILER:

@@ -121,6 +121,7 @@ typedef struct ac_lstm_tc_desc {
     void* final_hi; void* final_lo;         /* bf16, clip stride final_bstride */
     int64_t skip_bstride, final_bstride;
     int32_t final_act, batch, steps, hidden;
+    void* dbg;                 /* optional int64 [steps][8] clock samples (profiling aid), else NULL */
 } ac_lstm_tc_desc;
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
 
@@ -218,6 +219,23 @@ AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
  */
 AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
                             int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream);
+
+/*
+ * Edge layers of the bf16 pipeline (HBM-bound, SIMT):
+ * first: y[b][t][c] = bias[c] + sum_j w[j][c] * x[b][pad(t + j - pad_left)]   (Cin = 1; fp32 waveform in, bf16 out:
+ *        raw copy `y` and/or `y_act` = act(y), act = ELU or Snake(alpha));  C in {32, 64, 96}, K <= 8.
+ *        vlen: optional per-clip valid length (padding mask, R/audiocodecs/encodec.py:84-89).
+ * last : y[b][t] = epi(bias + sum_j sum_c w[j][c] * x[b][pad(t + j - pad_left)][c])   (Cout = 1; bf16 in, fp32 out).
+ * Replace the first/last conv of EncodecEncoder/Decoder (HF/encodec:289,341), MimiEncoder/Decoder (HF/mimi:461,1169),
+ * DacEncoder/Decoder (HF/dac:449,434-437).
+ */
+AC_API int ac_conv_first_bf16(const float* x, const float* w, const float* bias, const float* alpha, const int32_t* vlen,
+                              void* y, void* y_act, int64_t y_bstride, int64_t y_act_bstride, int32_t batch, int32_t T,
+                              int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len, int32_t act,
+                              void* stream);
+AC_API int ac_conv_last_bf16(const void* x, const float* w, const float* bias, float* y, int64_t x_bstride, int32_t batch,
+                             int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len,
+                             int32_t epi, void* stream);
 
 AC_API int ac_abi_version(void);
 AC_API const char* ac_last_error(void);

@@ -65,7 +65,7 @@ def test_end_to_end_code_match_report(encodec_sd, dev):
     assert tuple(rec.shape) == (4, 48000) and torch.isfinite(rec).all()
 
 
-@pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12)])
+@pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12), (70, 9)])
 def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T):
     """tcgen05 cluster LSTM (bf16 W_hh and h operands, fp32 accumulate / cell state) vs the oracle's explicit loop."""
     from audiocodecs_b200 import ops
