@@ -3,7 +3,9 @@
 Drop-in for `audiocodecs.{Encodec,DAC,Mimi}` `sig_to_toks` / `toks_to_sig` (R/audiocodecs/codec.py:57-66,90-100).
 """
 from .codec import Codec
+from .dac import DAC
 from .encodec import Encodec
+from .mimi import Mimi
 
 __version__ = "0.1.0"
-__all__ = ["Codec", "Encodec"]
+__all__ = ["Codec", "Encodec", "DAC", "Mimi"]

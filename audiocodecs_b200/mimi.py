@@ -1,0 +1,204 @@
+"""Mimi behind the reference's `Mimi` wrapper interface (R/audiocodecs/mimi.py:27-155).
+
+Same constructor arguments and tensor shapes; the `transformers.MimiModel` arithmetic
+(HF/mimi/modeling_mimi.py) is replaced by the sm_100a kernels of this package.  The wrapper never enables
+Mimi's streaming mode (R/audiocodecs/mimi.py:105-107): whole clip in one call.
+"""
+import math
+
+import torch
+
+from . import ops, packing
+from .codec import Codec
+from .ops import ACT_ELU, ACT_NONE, EPI_GELU, PAD_REPLICATE, PAD_ZERO, ConvSpec
+
+__all__ = ["Mimi"]
+
+RATIOS = (8, 6, 5, 4)  # MimiConfig().upsampling_ratios
+HID, HEADS, HEAD_DIM, WINDOW, LAYERS = 512, 8, 64, 250, 8
+
+
+class Mimi(Codec):
+    """`Mimi(sample_rate, mode="reconstruct", num_codebooks=8, latent=True)`; extra keywords `state_dict`
+    (`transformers.MimiModel` key format; default: fetch kyutai/mimi like the reference, mimi.py:45) and `precision`."""
+
+    def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32"):
+        super().__init__(sample_rate, 24000, mode)
+        if precision not in ("fp32",):
+            raise ValueError("Mimi currently runs on the exact fp32 path only (precision='fp32')")
+        self.num_codebooks = num_codebooks
+        self.vocab_size = 2048
+        self.latent = latent
+        self.precision = precision
+        self.compute_dtype = "f32"
+        if state_dict is None:
+            try:
+                from transformers import MimiModel
+            except ImportError:
+                raise ImportError("`pip install transformers>=4.45.1` to use this module")
+            state_dict = MimiModel.from_pretrained("kyutai/mimi").state_dict()
+        self._build(state_dict)
+
+    # ------------------------------------------------------------------ packing
+    def _conv(self, sd, prefix, stride=1, act=ACT_NONE, pad_mode=PAD_ZERO, scale=None, epi=ops.EPI_NONE):
+        w = packing.fold_weight_norm(sd, prefix)
+        if w.dim() == 2:
+            w = w[:, :, None]
+        if scale is not None:  # layer-scale folded into the producing projection (HF/mimi:499-511)
+            w = w * scale.float().view(-1, 1, 1)
+        cout, _, k = w.shape
+        bias = sd.get(prefix + ".bias")
+        spec = ConvSpec(packing.pack_conv(w), bias.float().clone() if bias is not None else None, cout=cout, kernel=k,
+                        stride=stride, geometry="causal", pad_mode=pad_mode, act=act, epi=epi)
+        self._specs.append(spec)
+        return spec
+
+    def _convtr(self, sd, prefix, stride, act):
+        w = packing.fold_weight_norm(sd, prefix)  # [Cin, Cout, 2s]
+        spec = ConvSpec(packing.pack_convtr(w, stride), sd[prefix + ".bias"].float().repeat(stride), cout=w.shape[1],
+                        geometry="tr", tr_stride=stride, tr_pad=0, act=act)
+        self._specs.append(spec)
+        return spec
+
+    def _transformer(self, sd, name):
+        layers = []
+        for l in range(LAYERS):
+            p = f"{name}.layers.{l}."
+            qkv_w = torch.cat([sd[p + f"self_attn.{w}.weight"].float() for w in ("q_proj", "k_proj", "v_proj")], dim=0)
+            sd_l = {"qkv.weight": qkv_w}
+            qkv = self._conv(sd_l, "qkv")
+            o = self._conv(sd, p + "self_attn.o_proj", scale=sd[p + "self_attn_layer_scale.scale"])
+            fc1 = self._conv(sd, p + "mlp.fc1", epi=EPI_GELU)
+            fc2 = self._conv(sd, p + "mlp.fc2", scale=sd[p + "mlp_layer_scale.scale"])
+            ln = []
+            for i, nm in enumerate(("input_layernorm", "post_attention_layernorm")):
+                for j, part in enumerate(("weight", "bias")):
+                    key = f"{name.split('_')[0]}_l{l}_ln{i}_{part}"
+                    self.register_buffer(key, sd[p + nm + "." + part].float().contiguous(), persistent=False)
+                    ln.append(key)
+            layers.append((ln, qkv, o, fc1, fc2))
+        return layers
+
+    def _build(self, sd):
+        self._specs = []
+        if self.mode != "decode":  # R/audiocodecs/mimi.py:46-51
+            enc = [self._conv(sd, "encoder.layers.0.conv")]
+            idx = 1
+            for r in reversed(RATIOS):
+                enc.append((self._conv(sd, f"encoder.layers.{idx}.block.1.conv", act=ACT_ELU),
+                            self._conv(sd, f"encoder.layers.{idx}.block.3.conv", act=ACT_ELU)))
+                enc.append(self._conv(sd, f"encoder.layers.{idx + 2}.conv", stride=r, act=ACT_ELU))
+                idx += 3
+            enc.append(self._conv(sd, f"encoder.layers.{idx + 1}.conv", act=ACT_ELU))
+            self._enc = enc
+            self._enc_tr = self._transformer(sd, "encoder_transformer")
+            self._down = self._conv(sd, "downsample.conv", stride=2, pad_mode=PAD_REPLICATE)
+        if self.mode != "encode":
+            self.register_buffer("up_w", sd["upsample.conv.weight"].float()[:, 0, :].contiguous(), persistent=False)  # [C,4]
+            self._dec_tr = self._transformer(sd, "decoder_transformer")
+            dec = [self._conv(sd, "decoder.layers.0.conv")]
+            idx = 2
+            for r in RATIOS:
+                dec.append(self._convtr(sd, f"decoder.layers.{idx}.conv", r, ACT_ELU))
+                dec.append((self._conv(sd, f"decoder.layers.{idx + 1}.block.1.conv", act=ACT_ELU),
+                            self._conv(sd, f"decoder.layers.{idx + 1}.block.3.conv", act=ACT_ELU)))
+                idx += 3
+            dec.append(self._conv(sd, f"decoder.layers.{idx}.conv", act=ACT_ELU))
+            self._dec = dec
+        # quantizer: E = embed_sum / clamp(cluster_usage, 1e-5) (HF/mimi:1188-1195); semantic (1) then acoustic (31) codebooks
+        cbs = []
+        for which, n in (("semantic", 1), ("acoustic", 31)):
+            q = f"quantizer.{which}_residual_vector_quantizer."
+            for k in range(n):
+                cbs.append(sd[q + f"layers.{k}.codebook.embed_sum"].float()
+                           / sd[q + f"layers.{k}.codebook.cluster_usage"].float().clamp(min=1e-5)[:, None])
+            setattr(self, f"_{which}_in", self._conv(sd, q + "input_proj"))
+            setattr(self, f"_{which}_out", self._conv(sd, q + "output_proj"))
+        cb = torch.stack(cbs).contiguous()
+        self.register_buffer("codebooks", cb, persistent=False)                    # [32, 2048, 256]
+        self.register_buffer("cb_norm", cb.pow(2).sum(-1).contiguous(), persistent=False)
+        inv_freq = 1.0 / (10000.0 ** (torch.arange(0, HEAD_DIM, 2, dtype=torch.int64).float() / HEAD_DIM))  # HF/mimi:560-562
+        self.register_buffer("inv_freq", inv_freq, persistent=False)
+        self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
+
+    def _packed(self):
+        return self._specs
+
+    # ------------------------------------------------------------------ pieces
+    def _seanet(self, layers, x):
+        for layer in layers:
+            if isinstance(layer, tuple):  # MimiResnetBlock, identity shortcut (HF/mimi:412-451)
+                h = ops.conv(layer[0], x)
+                x = ops.conv(layer[1], h, res=x)
+            else:
+                x = ops.conv(layer, x)
+        return x
+
+    def _run_transformer(self, layers, h):
+        """h [B,T,512] (HF/mimi:926-993): h += ls1*o_proj(attn(LN(h))); h += ls2*fc2(gelu(fc1(LN(h))))."""
+        for ln, qkv, o, fc1, fc2 in layers:
+            x = ops.layernorm(h, getattr(self, ln[0]), getattr(self, ln[1]))
+            a = ops.attention(ops.conv(qkv, x), self.inv_freq, HEADS, HEAD_DIM, WINDOW)
+            h = ops.conv(o, a, res=h)
+            x = ops.layernorm(h, getattr(self, ln[2]), getattr(self, ln[3]))
+            h = ops.conv(fc2, ops.conv(fc1, x), res=h)
+        return h
+
+    def _embeddings(self, sig):
+        """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
+        x = self._seanet(self._enc, sig.contiguous()[:, :, None])
+        x = self._run_transformer(self._enc_tr, x)
+        return ops.conv(self._down, x)
+
+    def _check_k(self, K):
+        if K > 32:
+            raise ValueError(f"The number of quantizers (i.e codebooks) asked should be lower than the total number of quantizers 32, but is currently {K}.")
+        if K < 1:
+            raise ValueError(f"The number of quantizers (i.e codebooks) asked should be higher than the number of semantic quantizers 1, but is currently {K}.")
+
+    # ------------------------------------------------------------------ Codec hooks
+    @torch.no_grad()
+    def embs(self):  # R/audiocodecs/mimi.py:55-90
+        e = self.codebooks[: self.num_codebooks].clone()
+        if self.latent:
+            return e
+        K = self.num_codebooks
+        sem = ops.conv(self._semantic_out, e[:1].contiguous())
+        if K == 1:
+            return sem
+        return torch.cat([sem, ops.conv(self._acoustic_out, e[1:].contiguous())])
+
+    def _sig_to_toks(self, sig, length):
+        K = self.num_codebooks
+        self._check_k(K)
+        emb = self._embeddings(sig)
+        B, N, _ = emb.shape
+        toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
+        xs = ops.conv(self._semantic_in, emb)
+        ops.rvq_encode(xs.view(B * N, -1), self.codebooks[:1], self.cb_norm[:1], toks.view(B * N, K), 1, code_offset=0, metric=1)
+        if K > 1:
+            xa = ops.conv(self._acoustic_in, emb)
+            ops.rvq_encode(xa.view(B * N, -1), self.codebooks[1:], self.cb_norm[1:], toks.view(B * N, K), K - 1, code_offset=1, metric=1)
+        return toks
+
+    def _sig_to_feats(self, sig, length):  # R/audiocodecs/mimi.py:112-121
+        return self._embeddings(sig)
+
+    def _sig_to_qfeats(self, sig, length):  # R/audiocodecs/mimi.py:124-141
+        return self._toks_to_qfeats(self._sig_to_toks(sig, length), length)
+
+    def _toks_to_qfeats(self, toks, length):  # R/audiocodecs/mimi.py:151-155 ; HF/mimi:1340-1349
+        B, N, K = toks.shape
+        toks = toks.to(torch.int64).contiguous()
+        sem = ops.rvq_decode(toks.view(B * N, K), self.codebooks[:1], 1, code_offset=0, err_flag=self._err).view(B, N, -1)
+        out = ops.conv(self._semantic_out, sem)
+        if K > 1:
+            ac = ops.rvq_decode(toks.view(B * N, K), self.codebooks[1:], K - 1, code_offset=1, err_flag=self._err).view(B, N, -1)
+            out = ops.conv(self._acoustic_out, ac, res=out, out=out)
+        return out
+
+    def _toks_to_sig(self, toks, length):  # R/audiocodecs/mimi.py:144-148 ; HF/mimi:1613-1631
+        z = self._toks_to_qfeats(toks, length)
+        z = ops.upsample_dw(z, self.up_w)
+        z = self._run_transformer(self._dec_tr, z)
+        return self._seanet(self._dec, z)[:, :, 0]

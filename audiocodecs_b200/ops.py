@@ -27,16 +27,18 @@ class Profiler:
         e.record()
         return e
 
-    def end(self, name, start, flops=0.0, bytes_=0.0):
+    def end(self, name, start, flops=0.0, bytes_=0.0, label=None):
+        """name = kernel (as ncu lists it); label = which layer family launched it; flops/bytes = ALGORITHMIC work of
+        the reference op (2 FLOP per MAC; activation bytes in+out once, 2 B each on the bf16 path -- SURVEY 8d)."""
         e = torch.cuda.Event(enable_timing=True)
         e.record()
-        self.records.append((name, start, e, flops, bytes_))
+        self.records.append((name, start, e, flops, bytes_, label or name))
 
-    def summary(self):
+    def summary(self, by_label=False):
         torch.cuda.synchronize()
         out = {}
-        for name, s, e, fl, by in self.records:
-            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        for name, s, e, fl, by, label in self.records:
+            d = out.setdefault(label if by_label else name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
             d["bytes"] += by
@@ -253,7 +255,7 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE,
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
     if _PROFILER:
-        _PROFILER.end("lstm_tc", t0, 2.0 * B * T * C4 * (C4 // 4), 4.0 * pre.numel() + 2.0 * B * T * (C4 // 4))
+        _PROFILER.end("lstm_tc_kernel", t0, 2.0 * B * T * C4 * (C4 // 4), 4.0 * pre.numel() + 2.0 * B * T * (C4 // 4))
 
 
 def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=None):
@@ -335,4 +337,71 @@ def resample(sig, orig_freq, new_freq):
     out = torch.empty((B, out_len), device=sig.device, dtype=torch.float32)
     _lib.check(_lib.lib().ac_resample_f32(_ptr(sig), _ptr(taps), _ptr(out), B, T, out_len, o, n, taps.shape[1], width,
                                           _stream()), "ac_resample_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- Mimi transformer pieces
+def layernorm(x, w, b, eps=1e-5):
+    """x [..., C] fp32 contiguous."""
+    _need_cuda(x, w, b)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    y = torch.empty_like(x)
+    C = x.shape[-1]
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_layernorm_f32(_ptr(x), _ptr(w), _ptr(b), _ptr(y), x.numel() // C, C, eps, _stream()), "ac_layernorm_f32")
+    if _PROFILER:
+        _PROFILER.end("layernorm_f32_kernel", t0, 0.0, 8.0 * x.numel())
+    return y
+
+
+def attention(qkv, inv_freq, heads, head_dim, window):
+    """qkv [B,T,3*H*D] fp32 -> [B,T,H*D]; RoPE + causal sliding-window softmax attention."""
+    _need_cuda(qkv, inv_freq)
+    B, T, _ = qkv.shape
+    assert qkv.is_contiguous() and qkv.shape[2] == 3 * heads * head_dim
+    out = torch.empty((B, T, heads * head_dim), device=qkv.device, dtype=torch.float32)
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_attention_f32(_ptr(qkv), _ptr(inv_freq), _ptr(out), B, T, heads, head_dim, window,
+                                           1.0 / math.sqrt(head_dim), _stream()), "ac_attention_f32")
+    if _PROFILER:
+        _PROFILER.end("attention_f32_kernel", t0, 4.0 * B * heads * head_dim * T * min(T, window) / 2, 4.0 * (qkv.numel() + out.numel()))
+    return out
+
+
+def upsample_dw(x, w):
+    """x [B,L,C] fp32, w [C,4] -> [B,2L,C] (depthwise ConvTranspose1d k4 s2, causal trim)."""
+    _need_cuda(x, w)
+    B, L, C = x.shape
+    y = torch.empty((B, 2 * L, C), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ac_upsample_dw_f32(_ptr(x.contiguous()), _ptr(w), _ptr(y), B, L, C, _stream()), "ac_upsample_dw_f32")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------- DAC RVQ
+def dac_rvq_encode(z, w_in, b_in, cb, w_out, b_out, stages, want_zq=False):
+    """z [B,N,1024] fp32 -> codes [B,N,stages] int64 (and the quantised sum [B,N,1024])."""
+    _need_cuda(z, w_in)
+    B, N, H = z.shape
+    codes = torch.empty((B, N, stages), device=z.device, dtype=torch.int64)
+    zq = torch.empty_like(z) if want_zq else None
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_dac_rvq_encode_f32(_ptr(z.contiguous()), _ptr(w_in), _ptr(b_in), _ptr(cb), _ptr(w_out), _ptr(b_out),
+                                                _ptr(codes), _ptr(zq), B * N, H, cb.shape[2], cb.shape[1], stages, stages,
+                                                _stream()), "ac_dac_rvq_encode_f32")
+    if _PROFILER:
+        _PROFILER.end("dac_rvq_encode_kernel", t0, 2.0 * B * N * stages * (2 * H * 8 + 8 * cb.shape[1]), 4.0 * z.numel())
+    return (codes, zq) if want_zq else codes
+
+
+def dac_rvq_decode(codes, cb, w_out, b_out, err_flag=None):
+    """codes [B,N,K] int64 -> z [B,N,1024] fp32 (from_codes)."""
+    _need_cuda(codes, cb)
+    B, N, K = codes.shape
+    codes = codes.to(torch.int64).contiguous()
+    out = torch.empty((B, N, w_out.shape[1]), device=codes.device, dtype=torch.float32)
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_dac_rvq_decode_f32(_ptr(codes), _ptr(cb), _ptr(w_out), _ptr(b_out), _ptr(out), B * N, w_out.shape[1],
+                                                cb.shape[2], cb.shape[1], K, K, _ptr(err_flag), _stream()), "ac_dac_rvq_decode_f32")
+    if _PROFILER:
+        _PROFILER.end("dac_rvq_decode_kernel", t0, 2.0 * B * N * K * 8 * w_out.shape[1], 4.0 * out.numel())
     return out

@@ -142,6 +142,7 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_conv_tc(ctypes.byref(d), ops._stream()), "ac_conv_tc")
     if ops._PROFILER:
-        n_out = sum(o is not None for o in (y, y_act)) * 2 + (4 if y32 is not None else 0) + (2 if res is not None else 0)
-        by = sum(2.0 * B * s.rows * s.phases * s.act.C for s in srcs) + n_out * B * out_rows * out_ch + 2.0 * W.w.numel()
-        ops._PROFILER.end(name, t0, 2.0 * B * m_rows * W.n_total * W.k_total, by)
+        # algorithmic bytes: every logical input and the logical output once at 2 B (lo planes / raw+act copies are
+        # implementation overhead and are not counted)
+        by = sum(2.0 * B * s.rows * s.phases * s.act.C for s in srcs) + 2.0 * B * out_rows * out_ch
+        ops._PROFILER.end("conv_tc_kernel", t0, 2.0 * B * m_rows * W.n_total * W.k_total, by, label=name)

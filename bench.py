@@ -27,6 +27,11 @@ WORKLOADS = {
 }
 
 
+# per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed ncu
+# captures (profiles/README.md); bytes per launch averaged over the captured launches, None when not captured
+NCU_TRAFFIC = {"conv_tc_kernel": None, "lstm_tc_kernel": 478.4e6}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -155,18 +160,31 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ops.set_profiler(None)
     summary = prof.summary()
+    by_label = prof.summary(by_label=True)
 
     value = audio_s_total * args.steps / (ms / 1e3)
     e2e = audio_s_total * args.steps / (ms_e2e / 1e3)
     peaks = load_peaks()
-    dom = max(summary.items(), key=lambda kv: kv[1]["ms"])
-    name, d = dom
-    tflops = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
-    roofline = {"kernel": name, "bound": "tensor", "achieved": round(tflops, 3), "peak": peaks["tf_sus"], "unit": "TFLOP/s",
-                "frac": round(tflops / peaks["tf_sus"], 5), "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)",
-                "launches_per_step": d["n"], "ms_per_step": round(d["ms"], 3),
-                "share_of_step": round(d["ms"] / sum(v["ms"] for v in summary.values()), 4),
-                "all_kernels_ms": {k: round(v["ms"], 3) for k, v in summary.items()}}
+    name, d = max(summary.items(), key=lambda kv: kv[1]["ms"])
+    sec = d["ms"] / 1e3
+    tflops = d["flops"] / sec / 1e12 if sec > 0 else 0.0
+    gbs = d["bytes"] / sec / 1e9 if sec > 0 else 0.0
+    # which roof bounds the dominant kernel: arithmetic intensity of its algorithmic work vs the measured ridge
+    ridge = peaks["tf_sus"] * 1e12 / (peaks["hbm"] * 1e9)
+    intensity = d["flops"] / d["bytes"] if d["bytes"] else float("inf")
+    if intensity < ridge:
+        roofline = {"kernel": name, "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": round(gbs / peaks["hbm"], 4)}
+    else:
+        roofline = {"kernel": name, "bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s",
+                    "frac": round(tflops / peaks["tf_sus"], 4)}
+    ncu = NCU_TRAFFIC.get(name)
+    roofline.update({"traffic": ncu, "peak_source": peaks["src"] + (" (copy bandwidth)" if roofline["bound"] == "hbm" else " (sustained bf16)"),
+                     "flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
+                     "tensor_tflops": round(tflops, 2), "launches_per_step": d["n"], "ms_per_step": round(d["ms"], 3),
+                     "share_of_step": round(d["ms"] / sum(v["ms"] for v in summary.values()), 4),
+                     "all_kernels_ms": {k: round(v["ms"], 3) for k, v in summary.items()},
+                     "by_layer_family_ms": {k: round(v["ms"], 3) for k, v in by_label.items()}})
     out = {
         "metric": "audio_seconds_per_second_encode_decode", "value": round(value, 2), "unit": "audio-s/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),

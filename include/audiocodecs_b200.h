@@ -237,6 +237,35 @@ AC_API int ac_conv_last_bf16(const void* x, const float* w, const float* bias, f
                              int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len,
                              int32_t epi, void* stream);
 
+/*
+ * Mimi transformer pieces that are not GEMMs (fp32): LayerNorm over the channel axis; RoPE (theta from inv_freq,
+ * rotate-half form, positions 0..T-1) + causal sliding-window attention on a fused qkv tensor [B][T][3*H*D]
+ * (q | k | v); depthwise ConvTranspose1d(k=4, s=2, groups=C) trimmed right by 2 (the `upsample` layer).
+ * Replace HF/mimi/modeling_mimi.py:926-993 (layer), :645-736 (attention), :515-577 (rotary), :1433-1441 (upsample).
+ */
+AC_API int ac_layernorm_f32(const float* x, const float* w, const float* b, float* y, int64_t rows, int32_t C, float eps,
+                            void* stream);
+AC_API int ac_attention_f32(const float* qkv, const float* inv_freq, float* out, int32_t batch, int32_t T, int32_t heads,
+                            int32_t head_dim, int32_t window, float scaling, void* stream);
+AC_API int ac_upsample_dw_f32(const float* x, const float* w, float* y, int32_t batch, int32_t L, int32_t C, void* stream);
+
+/*
+ * DAC residual VQ (hidden 1024, codebook dim 8), all stages fused, fp32.
+ * encode: z [rows][1024]; w_in [S][8][1024], b_in [S][8], codebooks [S][n_codes][8], w_out [S][1024][8], b_out [S][1024];
+ *         codes int64 at codes[row*code_stride + k]; zq_out (optional) [rows][1024] = sum_k out_proj_k(.) (the
+ *         quantised representation `z` of dac.DAC.encode).
+ * decode: from_codes: out[row] = sum_k out_proj_k(codebook_k[code_k]).
+ * Replace descript-audio-codec 1.0.0 dac/nn/quantize.py ResidualVectorQuantize.forward / from_codes
+ * (twin: HF/dac/modeling_dac.py:122-170,281-369), called at R/audiocodecs/dac.py:96-98,126-128.
+ */
+AC_API int ac_dac_rvq_encode_f32(const float* z, const float* w_in, const float* b_in, const float* codebooks,
+                                 const float* w_out, const float* b_out, int64_t* codes, float* zq_out, int64_t rows,
+                                 int32_t hidden, int32_t cb_dim, int32_t n_codes, int32_t stages, int32_t code_stride,
+                                 void* stream);
+AC_API int ac_dac_rvq_decode_f32(const int64_t* codes, const float* codebooks, const float* w_out, const float* b_out,
+                                 float* out, int64_t rows, int32_t hidden, int32_t cb_dim, int32_t n_codes, int32_t stages,
+                                 int32_t code_stride, int32_t* err_flag, void* stream);
+
 AC_API int ac_abi_version(void);
 AC_API const char* ac_last_error(void);
 /* number of kernel launches issued through this library by the calling process (bench: gpu_launches) */

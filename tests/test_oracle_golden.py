@@ -44,3 +44,39 @@ def test_resample_oracle_matches_torchaudio(o, n):
     got = resample_ref.resample(x, o, n)
     assert got.shape == ref.shape
     assert (got - ref).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_mimi_oracle_matches_reference_golden(mimi_sd, mimi_golden, case):
+    from oracle import mimi_ref
+    c = mimi_golden["cases"][case]
+    sig = make_input(c["seed"], c["B"], c["T"])
+    with torch.no_grad():
+        toks, gaps, _ = mimi_ref.sig_to_toks(mimi_sd, sig, c["K"], c["sample_rate"], return_gaps=True)
+        rec = mimi_ref.toks_to_sig(mimi_sd, c["toks"].long(), c["sample_rate"])
+    ref_toks = c["toks"].long()
+    assert toks.shape == ref_toks.shape
+    assert (toks == ref_toks)[gaps > 1e-4].all()
+    assert rec.shape == c["rec"].shape
+    assert (rec - c["rec"]).abs().max() <= 1e-4 * max(1.0, c["rec"].abs().max().item())
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_dac_oracle_matches_reference_golden(dac_sd, dac_golden, case):
+    from oracle import dac_ref
+    c = dac_golden["cases"][case]
+    sig = make_input(c["seed"], c["B"], c["T"])
+    with torch.no_grad():
+        toks, gaps, _ = dac_ref.sig_to_toks(dac_sd, sig, c["K"], c["sample_rate"], 44100, return_gaps=True)
+        rec = dac_ref.toks_to_sig(dac_sd, c["toks"].long(), c["sample_rate"], 44100)
+    ref_toks = c["toks"].long()
+    assert toks.shape == ref_toks.shape
+    assert (toks == ref_toks)[gaps > 1e-4].all()
+    assert rec.shape == c["rec"].shape
+    assert (rec - c["rec"]).abs().max() <= 1e-4
+
+
+def test_mimi_invalid_num_codebooks(mimi_sd):
+    from oracle import mimi_ref
+    with pytest.raises(ValueError):
+        mimi_ref.rvq_encode(mimi_sd, torch.zeros(1, 512, 2), 33)
