@@ -46,6 +46,8 @@ struct TcParams {
     const float* bias;
     const float* alpha;
     const __nv_bfloat16* res;
+    const __nv_bfloat16* res_lo;  // optional lo plane of the residual
+    const float* res32;           // optional fp32 residual (Mimi's fp32 residual stream)
     __nv_bfloat16* y;
     __nv_bfloat16* y_act;
     __nv_bfloat16* y_lo;      // optional lo planes: lo = bf16(v - float(bf16(v)))
@@ -59,6 +61,17 @@ struct TcParams {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void add_bf16x8(float (&o)[8], const __nv_bfloat16* ptr) {
+    const uint4 r = *reinterpret_cast<const uint4*>(ptr);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+        o[2 * i] += __low2float(h2);
+        o[2 * i + 1] += __high2float(h2);
+    }
 }
 
 // lo plane of 8 values: bf16(v - float(hi)) where hi is the already-packed bf16 rounding of v
@@ -216,14 +229,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
                         for (int i = 0; i < 8; ++i) o[i] = ac::gelu_erf(o[i]);
                     }
                     if (p.res) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(p.res + (long long)b * p.res_bs + f);
-                        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                            o[2 * i] += __low2float(h2);
-                            o[2 * i + 1] += __high2float(h2);
-                        }
+                        add_bf16x8(o, p.res + (long long)b * p.res_bs + f);
+                        if (p.res_lo) add_bf16x8(o, p.res_lo + (long long)b * p.res_bs + f);
+                    }
+                    if (p.res32) {
+                        const float4* r = reinterpret_cast<const float4*>(p.res32 + (long long)b * p.res_bs + f);
+                        const float4 r0 = r[0], r1 = r[1];
+                        o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+                        o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
                     }
                     if (p.y32) {
                         float4* d = reinterpret_cast<float4*>(p.y32 + (long long)b * p.y32_bs + f);
@@ -404,6 +417,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     p.bias = d->bias; p.alpha = d->alpha;
     p.res = (const __nv_bfloat16*)d->res; p.y = (__nv_bfloat16*)d->y; p.y_act = (__nv_bfloat16*)d->y_act; p.y32 = d->y32;
     p.y_lo = (__nv_bfloat16*)d->y_lo; p.y_act_lo = (__nv_bfloat16*)d->y_act_lo;
+    p.res_lo = (const __nv_bfloat16*)d->res_lo; p.res32 = d->res32;
     AC_REQUIRE((!p.y_lo || p.y) && (!p.y_act_lo || p.y_act), "ac_conv_tc: lo plane without its hi plane");
     p.act = d->act; p.epi = d->epi; p.act_mod = d->act_mod > 0 ? d->act_mod : d->n_total;
     p.y_bs = d->y_bstride; p.ya_bs = d->y_act_bstride; p.y32_bs = d->y32_bstride; p.res_bs = d->res_bstride;

@@ -97,6 +97,7 @@ class TcWeights:
 
 
 def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32: torch.Tensor = None, res: Act = None,
+            res32: torch.Tensor = None,
             act=ops.ACT_NONE, epi=ops.EPI_NONE, alpha=None, act_mod=0, out_rows=None, out_ch=None, out_shift=0, bk=None,
             n_tile_hint=0, grid_hint=0, name="conv_tc"):
     """Launch one tap-GEMM.  Outputs are Acts (bf16, flat layout starting at their valid row 0) and/or a
@@ -133,7 +134,10 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
     if y_act is not None:
         d.y_act, d.y_act_bstride, d.y_act_lo = y_act.row_ptr(0), y_act.bstride, y_act.lo_ptr(0)
     if res is not None:
-        d.res, d.res_bstride = res.row_ptr(0), res.bstride
+        d.res, d.res_bstride, d.res_lo = res.row_ptr(0), res.bstride, res.lo_ptr(0)
+    if res32 is not None:
+        assert res is None and res32.is_contiguous() and res32.dtype == torch.float32 and res32[0].numel() == out_rows * out_ch
+        d.res32, d.res_bstride = res32.data_ptr(), res32.stride(0)
     if y32 is not None:
         assert y32.is_contiguous() and y32.dtype == torch.float32 and y32.shape[0] == B and y32[0].numel() == out_rows * out_ch
         d.y32, d.y32_bstride = y32.data_ptr(), y32.stride(0)

@@ -208,6 +208,8 @@ typedef struct ac_conv_tc_desc {
     int64_t out_shift, out_valid;
     int32_t batch, m_rows;
     int32_t n_tile_hint, grid_hint; /* 0 = automatic */
+    const void* res_lo;          /* optional lo plane of `res` */
+    const float* res32;          /* optional fp32 residual in the output's flat layout (clip stride res_bstride) */
 } ac_conv_tc_desc;
 
 AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
