@@ -2,17 +2,26 @@
 //
 //   acc[b][m][n] = sum over sources s, taps j, channels k :  A_s[b][m + j*dil_s + shift_s][k] * W[n][kcol(s,j,k)]
 //
-// A_s are channels-last bf16 activation views [batch][rows][phases*c0] described by 4-D TMA tensor
-// maps (c0, phase, row, batch): a stride-s conv with kernel 2s is the 2-tap GEMM over the view whose
-// row is s consecutive time steps (no im2col, no padded copy; zero padding is TMA out-of-bounds fill,
-// reflect padding lives in the producer-written halo rows of the activation buffer).  W is the packed
-// K-major weight matrix [n_total][k_total].  Per 128-row tile the accumulator lives in TMEM; a
-// persistent CTA runs three roles:
-//   warp 0   : TMA producer   (A box [128 x BK] + W box [n_tile x BK] per k-block into a smem ring)
-//   warp 1   : tcgen05.mma issuer (one lane), commits free the ring slot / publish the accumulator
-//   warps 2-5: epilogue: tcgen05.ld -> bias (+ residual) -> bf16 / fp32 stores, optional second
-//              output with the CONSUMER's activation (ELU / Snake) so no layer ever re-reads raw+act.
-// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// A_s are channels-last bf16 activation views [batch][rows][phases*c0] described by 4-D TMA tensor maps
+// (c0, phase, row, batch): a stride-s conv with kernel 2s is the 2-tap GEMM over the view whose row is s
+// consecutive time steps (no im2col, no padded copy; zero padding is TMA out-of-bounds fill, reflect padding
+// lives in the producer-written halo rows of the activation buffer).  W is the packed K-major weight matrix
+// [n_total][k_total] (optionally the error-compensating pair W_hi, W_lo).
+//
+// Data movement (v2):
+//  * an A block = [G*128 + (taps-1)*dil rows] x [bk channels] is loaded ONCE per tile and contraction chunk;
+//    every tap and every one of the G 128-row sub-tiles reads it through a tcgen05 shared-memory descriptor
+//    whose start address is advanced by whole rows (measured: the swizzle is a function of the absolute
+//    shared-memory address, so a row-shifted start needs no base offset -- scripts/probe_desc_shift.cu).
+//    A K-tap conv therefore moves its activations once instead of K times, and G sub-tiles share one barrier
+//    round trip and one weight block.
+//  * weights: small matrices (EnCodec/Mimi <=64-channel layers) are RESIDENT in shared memory for the whole
+//    kernel; large ones stream through their own ring, one [n_tile x bk] block (hi + lo) per tap and chunk,
+//    shared by the G sub-tiles.
+// Roles of the persistent CTA (one per SM): warp 0 = A producer, warp 1 = tcgen05.mma issuer (one lane),
+// warp 2 = W producer, warps 3-18 = epilogue (tcgen05.ld -> bias, residual, raw / activated / lo-plane bf16
+// or fp32 stores; the activation written is the CONSUMER's, so no layer re-reads a tensor just to activate it).
+// TMEM holds up to two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -23,37 +32,50 @@ namespace {
 using namespace sm100;
 
 constexpr int TILE_M = 128;
-constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over 16-column chunks
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
-
+constexpr int MAX_A_STAGES = 8;
+constexpr int MAX_W_STAGES = 6;
+constexpr int EPI_WARPS = 16;  // four warps per TMEM lane quarter
+constexpr int FIRST_EPI_WARP = 3;
+constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS);
 constexpr int MAX_SRC = 4;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct TcSrc {
-    int c0;      // innermost tensor-map dim (channels per phase)
+    int c0;        // innermost tensor-map dim (channels per phase)
     int taps, dil, shift;
-    int chunks;  // k-blocks per tap
-    int kb0;     // first weight k-block (a lo-plane source re-uses the columns of its hi twin)
-    int nb;      // weight tiles per k-block: 2 = W_hi and W_lo (hi-plane source, split weights), 1 = W_hi only
+    int chunks;    // k-blocks per tap
+    int kb0;       // first weight k-block of this source
+    int has_lo;    // lo plane present: adds the A_lo * W_hi product
+    int pieces, box_rows;  // the A block is loaded as `pieces` TMA boxes of box_rows rows
+};
+
+struct TcMaps {
+    CUtensorMap a[MAX_SRC];
+    CUtensorMap a_lo[MAX_SRC];
+    CUtensorMap w;
 };
 
 struct TcParams {
     TcSrc src[MAX_SRC];
     int n_src, bk, num_kb;
-    int n_total, n_tile, n_tiles, m_rows, m_tiles, batch;
-    int stages;
-    uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+    int n_total, n_tile, n_tiles, m_rows, m_groups, batch, G;
+    int a_stages, w_stages, acc_stages;
+    int w_resident, w_split;
+    uint32_t a_stage_bytes, a_plane_bytes;  // lo block sits a_plane_bytes after the hi block
+    uint32_t w_stage_bytes, w_plane_bytes;  // streaming ring: W_lo sits w_plane_bytes after W_hi
+    uint32_t w_kb_bytes, w_res_plane;       // resident: block kb at kb*w_kb_bytes, lo plane w_res_plane further
+    uint32_t tmem_cols;
     const float* bias;
     const float* alpha;
     const __nv_bfloat16* res;
     const __nv_bfloat16* res_lo;  // optional lo plane of the residual
-    const float* res32;           // optional fp32 residual (Mimi's fp32 residual stream)
+    const float* res32;           // optional fp32 residual
     __nv_bfloat16* y;
     __nv_bfloat16* y_act;
-    __nv_bfloat16* y_lo;      // optional lo planes: lo = bf16(v - float(bf16(v)))
+    __nv_bfloat16* y_lo;          // optional lo planes: lo = bf16(v - float(bf16(v)))
     __nv_bfloat16* y_act_lo;
     float* y32;
-    int w_rows;               // rows of one weight plane in the B tensor map (n_total); W_lo starts at row w_rows
+    int w_rows;                   // rows of one weight plane in the W tensor map (n_total); W_lo starts at row w_rows
     int act, epi, act_mod;
     long long y_bs, ya_bs, y32_bs, res_bs, out_shift, out_valid;
 };
@@ -86,70 +108,294 @@ __device__ __forceinline__ uint4 pack_lo(const float (&v)[8], const uint4& hi) {
     return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+    return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+}
+
+// ELU on the epilogue: exp through MUFU.EX2; abs error ~1e-7 (cancellation in exp(x)-1 near 0), far below the bf16 /
+// split-bf16 rounding that follows.
+__device__ __forceinline__ float elu_ex2(float x) { return x > 0.f ? x : exp2f(x * 1.4426950408889634f) - 1.0f; }
+
+// Epilogue warps: each item is one tcgen05.ld of 32 rows x 16 accumulator columns (lane = row).  The sixteen warps
+// (four per TMEM lane quarter) interleave over the (sub-tile, column chunk) items of the tile.
+template <int ACT>
+__device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane,
+                                         int total_tiles) {
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+    const int slot = (warp - FIRST_EPI_WARP) >> 2;   // 0..3
+    const int chunks_n = p.n_tile / 16;
+    const int items = p.G * chunks_n;
+    const bool has_res = p.res != nullptr, has_res_lo = p.res_lo != nullptr, has_res32 = p.res32 != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int mg = rest % p.m_groups;
+        const int b = rest / p.m_groups;
+        const int as = p.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tfull[as], tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.G * p.n_tile;
+        for (int item = slot; item < items; item += EPI_WARPS / 4) {
+            const int g = item / chunks_n, c = item - g * chunks_n;
+            uint32_t v[16];
+            tmem_ld16(taddr + g * p.n_tile + c * 16, v);
+            const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
+            const int n0 = nt * p.n_tile + c * 16;
+            const long long flat = (long long)m * p.n_total + n0 - p.out_shift;
+            const bool ok = m < p.m_rows && n0 < p.n_total;
+            tmem_ld_wait();
+            if (!ok) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // two 8-element vectors (16 B of bf16 each)
+                const long long f = flat + h * 8;
+                const int n = n0 + h * 8;
+                if (f < 0 || f >= p.out_valid || n >= p.n_total) continue;
+                float o[8];
+                if (p.bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[h * 8 + i]) + bb[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[h * 8 + i]);
+                }
+                if (p.epi == AC_EPI_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = ac::gelu_erf(o[i]);
+                }
+                if (has_res) {
+                    add_bf16x8(o, p.res + (long long)b * p.res_bs + f);
+                    if (has_res_lo) add_bf16x8(o, p.res_lo + (long long)b * p.res_bs + f);
+                }
+                if (has_res32) {
+                    const float4* r = reinterpret_cast<const float4*>(p.res32 + (long long)b * p.res_bs + f);
+                    const float4 r0 = r[0], r1 = r[1];
+                    o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+                    o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+                }
+                if (p.y32) {
+                    float4* d = reinterpret_cast<float4*>(p.y32 + (long long)b * p.y32_bs + f);
+                    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (p.y) {
+                    const uint4 q = pack8(o);
+                    *reinterpret_cast<uint4*>(p.y + (long long)b * p.y_bs + f) = q;
+                    if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + (long long)b * p.y_bs + f) = pack_lo(o, q);
+                }
+                if (p.y_act) {
+                    float a[8];
+                    if (ACT == AC_ACT_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a[i] = elu_ex2(o[i]);
+                    } else if (ACT == AC_ACT_SNAKE) {
+                        // the channel of column n is n % act_mod; act_mod % 8 == 0 so a vector never wraps
+                        const float* ap = p.alpha + (n % p.act_mod);
+                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap));
+                        const float4 a1 = __ldg(reinterpret_cast<const float4*>(ap) + 1);
+                        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float sn = __sinf(al[i] * o[i]);
+                            a[i] = fmaf(__frcp_rn(al[i] + 1e-9f), sn * sn, o[i]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a[i] = o[i];
+                    }
+                    const uint4 q = pack8(a);
+                    *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + f) = q;
+                    if (p.y_act_lo) *reinterpret_cast<uint4*>(p.y_act_lo + (long long)b * p.ya_bs + f) = pack_lo(a, q);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+}
+
+// MMA issuer warp.  The whole warp walks the (uniform) loop nest and waits on the barriers; one elected lane issues
+// tcgen05.mma / tcgen05.commit.  Keeping control flow and operands warp-uniform lets ptxas hold the descriptors in
+// uniform registers -- a divergent single-lane loop costs ~25 SASS instructions per MMA (measured: the issuer thread,
+// not the tensor pipe or HBM, bounded the <=64-channel layers).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uint8_t* w_area, uint64_t* a_full, uint64_t* a_empty,
+                                         uint64_t* w_full, uint64_t* w_empty, uint64_t* tfull, uint64_t* tempty, uint64_t* wres_bar,
+                                         uint32_t tmem_base, int total_tiles) {
+    const bool leader = elect_one();
+    int astage = 0, wstage = 0;
+    uint32_t aphase = 0, wphase = 0;
+    const uint32_t idesc = make_idesc_bf16(TILE_M, p.n_tile);
+    const uint32_t row_bytes = KSTEPS * 32;
+    const uint64_t desc_base = make_smem_desc(0, row_bytes);  // everything but the start address
+    const uint32_t a_ring_u = smem_u32(a_ring), w_area_u = smem_u32(w_area);
+    if (p.w_resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = p.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tempty[as], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + as * p.G * p.n_tile;
+        uint32_t acc = 0;  // first MMA into each accumulator overwrites
+        for (int s = 0; s < p.n_src; ++s) {
+            const TcSrc& S = p.src[s];
+            const int taps = S.taps, chunks = S.chunks, has_lo = S.has_lo;
+            const uint32_t dil_bytes = S.dil * row_bytes;
+            for (int cc = 0; cc < chunks; ++cc) {
+                mbar_wait(&a_full[astage], aphase);
+                tc_fence_after();
+                const uint32_t a_hi = a_ring_u + astage * p.a_stage_bytes;
+                for (int j = 0; j < taps; ++j) {
+                    uint32_t w_hi, w_lo;
+                    if (p.w_resident) {
+                        w_hi = w_area_u + (S.kb0 + j * chunks + cc) * p.w_kb_bytes;
+                        w_lo = w_hi + p.w_res_plane;
+                    } else {
+                        mbar_wait(&w_full[wstage], wphase);
+                        tc_fence_after();
+                        w_hi = w_area_u + wstage * p.w_stage_bytes;
+                        w_lo = w_hi + p.w_plane_bytes;
+                    }
+                    const uint64_t bdesc_hi = desc_base | ((w_hi & 0x3FFFFu) >> 4);
+                    const uint64_t bdesc_lo = desc_base | ((w_lo & 0x3FFFFu) >> 4);
+                    uint32_t a_addr = a_hi + j * dil_bytes;
+                    uint32_t d_tmem = d_base;
+                    for (int g = 0; g < p.G; ++g, a_addr += TILE_M * row_bytes, d_tmem += p.n_tile) {
+                        const uint64_t adesc = desc_base | ((a_addr & 0x3FFFFu) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc_hi + 2 * k, idesc, k == 0 ? acc : 1u);  // +32 B per K=16
+                            if (p.w_split) {  // error-compensated weights: A * W_lo into the same accumulator
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
+                            }
+                            if (has_lo) {  // split activations: A_lo * W_hi (A_lo * W_lo is below fp32 noise)
+                                const uint64_t adesc_lo = desc_base | (((a_addr + p.a_plane_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc_lo + 2 * k, bdesc_hi + 2 * k, idesc, 1u);
+                            }
+                        }
+                    }
+                    acc = 1u;
+                    if (!p.w_resident) {
+                        if (leader) umma_commit(&w_empty[wstage]);
+                        if (++wstage == p.w_stages) { wstage = 0; wphase ^= 1; }
+                    }
+                }
+                if (leader) umma_commit(&a_empty[astage]);  // frees the A block when the MMAs retire
+                if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+            }
+        }
+        if (leader) umma_commit(&tfull[as]);  // accumulators complete
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
-               const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap amap3,
-               const __grid_constant__ CUtensorMap bmap, const TcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 for the swizzled tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + (size_t)p.stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.stages * p.b_stage_bytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + MAX_STAGES;
-    uint64_t* tfull = bars + 2 * MAX_STAGES;
-    uint64_t* tempty = bars + 2 * MAX_STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
-    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [n_total] (<= 8192 floats reserved by the host)
+    uint8_t* w_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
+    const size_t w_area_bytes = p.w_resident ? (size_t)p.w_res_plane * (1 + p.w_split) : (size_t)p.w_stages * p.w_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_area + w_area_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + MAX_A_STAGES;
+    uint64_t* w_full = a_empty + MAX_A_STAGES;
+    uint64_t* w_empty = w_full + MAX_W_STAGES;
+    uint64_t* tfull = w_empty + MAX_W_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wres_bar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.n_tiles * p.m_tiles * p.batch;
+    const int total_tiles = p.n_tiles * p.m_groups * p.batch;
+    const uint32_t row_bytes = p.bk * 2;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&amap0);
-        if (p.n_src > 1) prefetch_tensormap(&amap1);
-        if (p.n_src > 2) prefetch_tensormap(&amap2);
-        if (p.n_src > 3) prefetch_tensormap(&amap3);
-        prefetch_tensormap(&bmap);
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int s = 0; s < p.n_src; ++s) {
+            prefetch_tensormap(&maps.a[s]);
+            if (p.src[s].has_lo) prefetch_tensormap(&maps.a_lo[s]);
+        }
+        prefetch_tensormap(&maps.w);
+        for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+        mbar_init(wres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.n_total; i += THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================================================================= TMA producer
+        // ================================================================= A producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t a_tx = TILE_M * p.bk * 2, b_tx = p.n_tile * p.bk * 2;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
                 const int rest = tile / p.n_tiles;
-                const int mt = rest % p.m_tiles;
-                const int b = rest / p.m_tiles;
+                const int mg = rest % p.m_groups;
+                const int b = rest / p.m_groups;
                 for (int s = 0; s < p.n_src; ++s) {
                     const TcSrc& S = p.src[s];
-                    const CUtensorMap* am = s == 0 ? &amap0 : (s == 1 ? &amap1 : (s == 2 ? &amap2 : &amap3));
-                    int kb = S.kb0;
-                    for (int j = 0; j < S.taps; ++j) {
-                        const int row = mt * TILE_M + j * S.dil + S.shift;
-                        for (int cc = 0; cc < S.chunks; ++cc, ++kb) {
-                            mbar_wait(&empty[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&full[stage], a_tx + S.nb * b_tx);
-                            const int flat = cc * p.bk;
-                            uint8_t* bs = b_ring + (size_t)stage * p.b_stage_bytes;
-                            tma_load_4d(a_ring + (size_t)stage * p.a_stage_bytes, am, &full[stage], flat % S.c0, flat / S.c0, row, b);
-                            tma_load_2d(bs, &bmap, &full[stage], kb * p.bk, nt * p.n_tile);
-                            if (S.nb == 2) tma_load_2d(bs + p.b_stage_bytes / 2, &bmap, &full[stage], kb * p.bk, p.w_rows + nt * p.n_tile);
-                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    const int row0 = mg * p.G * TILE_M + S.shift;
+                    const uint32_t piece_bytes = S.box_rows * row_bytes;
+                    for (int cc = 0; cc < S.chunks; ++cc) {
+                        mbar_wait(&a_empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&a_full[stage], S.pieces * piece_bytes * (1 + S.has_lo));
+                        const int flat = cc * p.bk;
+                        uint8_t* dst = a_ring + (size_t)stage * p.a_stage_bytes;
+                        for (int pc = 0; pc < S.pieces; ++pc) {
+                            tma_load_4d(dst + pc * piece_bytes, &maps.a[s], &a_full[stage], flat % S.c0, flat / S.c0,
+                                        row0 + pc * S.box_rows, b);
+                            if (S.has_lo)
+                                tma_load_4d(dst + p.a_plane_bytes + pc * piece_bytes, &maps.a_lo[s], &a_full[stage], flat % S.c0,
+                                            flat / S.c0, row0 + pc * S.box_rows, b);
+                        }
+                        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================================================= W producer
+        if (lane == 0) {
+            const uint32_t blk_bytes = p.n_tile * row_bytes;
+            if (p.w_resident) {
+                // whole matrix once: block kb = [n_total x bk] at kb * w_kb_bytes, lo plane after all hi blocks
+                mbar_arrive_expect_tx(wres_bar, (uint32_t)p.num_kb * blk_bytes * (1 + p.w_split));
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    tma_load_2d(w_area + (size_t)kb * p.w_kb_bytes, &maps.w, wres_bar, kb * p.bk, 0);
+                    if (p.w_split) tma_load_2d(w_area + p.w_res_plane + (size_t)kb * p.w_kb_bytes, &maps.w, wres_bar, kb * p.bk, p.w_rows);
+                }
+            } else {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int nt = tile % p.n_tiles;
+                    for (int s = 0; s < p.n_src; ++s) {
+                        const TcSrc& S = p.src[s];
+                        for (int cc = 0; cc < S.chunks; ++cc) {
+                            for (int j = 0; j < S.taps; ++j) {
+                                const int kb = S.kb0 + j * S.chunks + cc;
+                                mbar_wait(&w_empty[stage], phase ^ 1);
+                                mbar_arrive_expect_tx(&w_full[stage], blk_bytes * (1 + p.w_split));
+                                uint8_t* dst = w_area + (size_t)stage * p.w_stage_bytes;
+                                tma_load_2d(dst, &maps.w, &w_full[stage], kb * p.bk, nt * p.n_tile);
+                                if (p.w_split) tma_load_2d(dst + p.w_plane_bytes, &maps.w, &w_full[stage], kb * p.bk, p.w_rows + nt * p.n_tile);
+                                if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+                            }
                         }
                     }
                 }
@@ -157,123 +403,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t idesc = make_idesc_bf16(TILE_M, p.n_tile);
-            const uint32_t sw = p.bk * 2;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty[as], aphase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * p.n_tile;
-                int kb = 0;
-                for (int s = 0; s < p.n_src; ++s) {
-                    const int nkb = p.src[s].taps * p.src[s].chunks;
-                    const int nb = p.src[s].nb;
-                    for (int i = 0; i < nkb; ++i, ++kb) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint64_t adesc = make_smem_desc(smem_u32(a_ring + (size_t)stage * p.a_stage_bytes), sw);
-                        const uint32_t b_addr = smem_u32(b_ring + (size_t)stage * p.b_stage_bytes);
-                        const uint64_t bdesc = make_smem_desc(b_addr, sw);
-                        for (int k = 0; k < p.bk / 16; ++k)
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);  // +32 B per K=16 step
-                        if (nb == 2) {  // error-compensated weights: A * W_lo into the same accumulator
-                            const uint64_t bdesc_lo = make_smem_desc(b_addr + p.b_stage_bytes / 2, sw);
-                            for (int k = 0; k < p.bk / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
-                        }
-                        umma_commit(&empty[stage]);                        // frees the ring slot when the MMAs retire
-                        if (kb == p.num_kb - 1) umma_commit(&tfull[as]);   // accumulator complete
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
+        if (p.bk == 64) mma_role<4>(p, a_ring, w_area, a_full, a_empty, w_full, w_empty, tfull, tempty, wres_bar, tmem_base, total_tiles);
+        else if (p.bk == 32) mma_role<2>(p, a_ring, w_area, a_full, a_empty, w_full, w_empty, tfull, tempty, wres_bar, tmem_base, total_tiles);
+        else mma_role<1>(p, a_ring, w_area, a_full, a_empty, w_full, w_empty, tfull, tempty, wres_bar, tmem_base, total_tiles);
     } else {
-        // ================================================================= epilogue (warps 2..9)
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-        const int chunk0 = (warp - 2) >> 2;  // this warp takes chunks chunk0, chunk0+2, ...
-        const int row_in_tile = quarter * 32 + lane;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int nt = tile % p.n_tiles;
-            const int rest = tile / p.n_tiles;
-            const int mt = rest % p.m_tiles;
-            const int b = rest / p.m_tiles;
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
-            const int m = mt * TILE_M + row_in_tile;
-            const bool row_ok = m < p.m_rows;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.n_tile;
-            for (int c = chunk0; c < p.n_tile / 16; c += EPI_WARPS / 4) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c * 16, v);
-                tmem_ld_wait();
-                const int n0 = nt * p.n_tile + c * 16;
-                if (!row_ok || n0 >= p.n_total) continue;
-                const long long flat = (long long)m * p.n_total + n0 - p.out_shift;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {  // two 8-element vectors (16 B of bf16 each)
-                    const long long f = flat + h * 8;
-                    if (f < 0 || f >= p.out_valid || n0 + h * 8 >= p.n_total) continue;
-                    float o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[h * 8 + i]) + bias_s[n0 + h * 8 + i];
-                    if (p.epi == AC_EPI_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = ac::gelu_erf(o[i]);
-                    }
-                    if (p.res) {
-                        add_bf16x8(o, p.res + (long long)b * p.res_bs + f);
-                        if (p.res_lo) add_bf16x8(o, p.res_lo + (long long)b * p.res_bs + f);
-                    }
-                    if (p.res32) {
-                        const float4* r = reinterpret_cast<const float4*>(p.res32 + (long long)b * p.res_bs + f);
-                        const float4 r0 = r[0], r1 = r[1];
-                        o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-                        o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-                    }
-                    if (p.y32) {
-                        float4* d = reinterpret_cast<float4*>(p.y32 + (long long)b * p.y32_bs + f);
-                        d[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        d[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    }
-                    if (p.y) {
-                        uint4 q;
-                        q.x = pack_bf16(o[0], o[1]); q.y = pack_bf16(o[2], o[3]);
-                        q.z = pack_bf16(o[4], o[5]); q.w = pack_bf16(o[6], o[7]);
-                        *reinterpret_cast<uint4*>(p.y + (long long)b * p.y_bs + f) = q;
-                        if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + (long long)b * p.y_bs + f) = pack_lo(o, q);
-                    }
-                    if (p.y_act) {
-                        float a[8];
-                        if (p.act == AC_ACT_ELU) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = ac::elu_fast(o[i]);
-                        } else if (p.act == AC_ACT_SNAKE) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = ac::snake(o[i], __ldg(p.alpha + (n0 + h * 8 + i) % p.act_mod));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) a[i] = o[i];
-                        }
-                        uint4 q;
-                        q.x = pack_bf16(a[0], a[1]); q.y = pack_bf16(a[2], a[3]);
-                        q.z = pack_bf16(a[4], a[5]); q.w = pack_bf16(a[6], a[7]);
-                        *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + f) = q;
-                        if (p.y_act_lo) *reinterpret_cast<uint4*>(p.y_act_lo + (long long)b * p.ya_bs + f) = pack_lo(a, q);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
-        }
+        // ================================================================= epilogue (warps 3..18)
+        if (p.act == AC_ACT_ELU) epilogue<AC_ACT_ELU>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
+        else if (p.act == AC_ACT_SNAKE) epilogue<AC_ACT_SNAKE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
+        else epilogue<AC_ACT_NONE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
     }
     tc_fence_before();
     __syncthreads();
@@ -315,6 +452,13 @@ int sm_count() {
     return sms;
 }
 
+inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+struct MergedSrc {
+    const ac_tc_src* hi;
+    const ac_tc_src* lo;
+};
+
 }  // namespace
 
 extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
@@ -324,96 +468,179 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
                "ac_conv_tc: bad sizes (batch %d rows %d n %d)", d->batch, d->m_rows, d->n_total);
     AC_REQUIRE(d->y || d->y_act || d->y32, "ac_conv_tc: no output");
     AC_REQUIRE(d->out_shift % 8 == 0 && d->out_valid % 8 == 0, "ac_conv_tc: out_shift/out_valid must be multiples of 8");
-    AC_REQUIRE(d->act != AC_ACT_SNAKE || (d->alpha && d->act_mod > 0), "ac_conv_tc: snake needs alpha/act_mod");
+    AC_REQUIRE(d->act != AC_ACT_SNAKE || (d->alpha && d->act_mod > 0 && d->act_mod % 8 == 0 && ((uintptr_t)d->alpha & 15) == 0),
+               "ac_conv_tc: snake needs a 16-byte aligned alpha and act_mod % 8 == 0");
+    AC_REQUIRE(!d->bias || ((uintptr_t)d->bias & 15) == 0, "ac_conv_tc: bias not 16-byte aligned");
     EncodeTiledFn encode = get_encode();
     AC_REQUIRE(encode, "ac_conv_tc: cuTensorMapEncodeTiled not available");
 
-    TcParams p{};
-    p.n_src = d->n_src;
-    p.bk = d->bk;
-    int k_total = 0, num_kb = 0;
-    const int w_split = d->w_split ? 1 : 0;
-    CUtensorMap amap[MAX_SRC];
+    // lo-plane twins (lo_of >= 0) are folded into their hi source: one A block carries both planes
+    MergedSrc ms[MAX_SRC];
+    int map_of[MAX_SRC];
+    int n_ms = 0;
     for (int s = 0; s < d->n_src; ++s) {
         const ac_tc_src& S = d->src[s];
-        AC_REQUIRE(S.base && S.c0 > 0 && S.phases > 0 && S.rows > 0 && S.taps > 0, "ac_conv_tc: bad source %d", s);
-        const int kper = S.c0 * S.phases;  // contraction length per tap
-        // a k-block never straddles two phases: a TMA box whose inner extent is narrower than the swizzle span
-        // does not land in the UMMA canonical layout (measured: tests/test_conv_tc_gpu.py history)
-        AC_REQUIRE(S.c0 % d->bk == 0, "ac_conv_tc: bk %d must divide c0 %d", d->bk, S.c0);
+        AC_REQUIRE(S.base && S.c0 > 0 && S.phases > 0 && S.rows > 0 && S.taps > 0 && S.dilation > 0, "ac_conv_tc: bad source %d", s);
         AC_REQUIRE(((uintptr_t)S.base & 15) == 0 && (S.phase_stride * 2) % 16 == 0 && (S.row_stride * 2) % 16 == 0 &&
                        (S.batch_stride * 2) % 16 == 0, "ac_conv_tc: source %d not 16-byte aligned", s);
-        p.src[s].c0 = S.c0;
-        p.src[s].taps = S.taps;
-        p.src[s].dil = S.dilation;
-        p.src[s].shift = S.shift;
-        p.src[s].chunks = kper / d->bk;
         if (S.lo_of >= 0) {
-            // lo plane of source lo_of: same weight columns, W_hi only (the A_lo * W_lo term is below fp32 noise)
-            AC_REQUIRE(S.lo_of < s && d->src[S.lo_of].c0 == S.c0 && d->src[S.lo_of].phases == S.phases &&
-                           d->src[S.lo_of].taps == S.taps, "ac_conv_tc: source %d is not the lo twin of %d", s, S.lo_of);
-            p.src[s].kb0 = p.src[S.lo_of].kb0;
-            p.src[s].nb = 1;
+            AC_REQUIRE(S.lo_of < s && d->src[S.lo_of].lo_of < 0, "ac_conv_tc: source %d: bad lo_of", s);
+            const ac_tc_src& H = d->src[S.lo_of];
+            AC_REQUIRE(H.c0 == S.c0 && H.phases == S.phases && H.taps == S.taps && H.rows == S.rows && H.dilation == S.dilation &&
+                           H.shift == S.shift, "ac_conv_tc: source %d is not the lo twin of %d", s, S.lo_of);
+            AC_REQUIRE(ms[map_of[S.lo_of]].lo == nullptr, "ac_conv_tc: source %d has two lo twins", S.lo_of);
+            ms[map_of[S.lo_of]].lo = &S;
+            map_of[s] = map_of[S.lo_of];
         } else {
-            p.src[s].kb0 = k_total / d->bk;
-            p.src[s].nb = 1 + w_split;
-            k_total += S.taps * kper;
+            map_of[s] = n_ms;
+            ms[n_ms].hi = &S;
+            ms[n_ms].lo = nullptr;
+            ++n_ms;
         }
-        num_kb += S.taps * p.src[s].chunks;
-        const int box0 = S.c0 < d->bk ? S.c0 : d->bk;
-        cuuint64_t gdim[4] = {(cuuint64_t)S.c0, (cuuint64_t)S.phases, (cuuint64_t)S.rows, (cuuint64_t)d->batch};
-        cuuint64_t gstr[3] = {(cuuint64_t)S.phase_stride * 2, (cuuint64_t)S.row_stride * 2, (cuuint64_t)S.batch_stride * 2};
-        cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)(d->bk / box0), TILE_M, 1};
-        cuuint32_t est[4] = {1, 1, 1, 1};
-        CUresult r = encode(&amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.base), gdim, gstr, box, est,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(d->bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        AC_REQUIRE(r == CUDA_SUCCESS, "ac_conv_tc: cuTensorMapEncodeTiled(A%d) failed: %d", s, (int)r);
     }
-    for (int s = d->n_src; s < MAX_SRC; ++s) amap[s] = amap[0];
-    AC_REQUIRE(k_total == d->k_total, "ac_conv_tc: k_total %d != sum of taps*channels %d", d->k_total, k_total);
-    p.num_kb = num_kb;
-    p.w_rows = d->n_total;
 
-    // N tile: the largest of {256,...,16} that does not over-pad
+    const int w_split = d->w_split ? 1 : 0;
+    // N tile: the largest of {256,...,16} that does not over-pad; split weights hold two W tiles per stage -> cap at 128
     int n_tile = 16;
-    // with split weights a stage holds two W tiles: cap the tile at 128 columns to keep >= 4 ring stages
     for (int c : {256, 192, 128, 96, 64, 48, 32, 16})
         if ((!w_split || c <= 128) && d->n_total % c == 0) { n_tile = c; break; }
     if (d->n_total % n_tile != 0) n_tile = d->n_total >= 128 ? 128 : 16;
     if (d->n_tile_hint > 0) n_tile = d->n_tile_hint;
     AC_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "ac_conv_tc: n_tile %d", n_tile);
-    p.n_total = d->n_total;
-    p.n_tile = n_tile;
-    p.n_tiles = (d->n_total + n_tile - 1) / n_tile;
-    p.m_rows = d->m_rows;
-    p.m_tiles = (d->m_rows + TILE_M - 1) / TILE_M;
-    p.batch = d->batch;
+    const int n_tiles = (d->n_total + n_tile - 1) / n_tile;
 
-    CUtensorMap bmap;
+    int k_total = 0;
+    bool any_lo = false;
+    int max_halo = 0;
+    for (int s = 0; s < n_ms; ++s) {
+        k_total += ms[s].hi->taps * ms[s].hi->c0 * ms[s].hi->phases;
+        any_lo |= ms[s].lo != nullptr;
+        const int halo = (ms[s].hi->taps - 1) * ms[s].hi->dilation;
+        if (halo > max_halo) max_halo = halo;
+    }
+    AC_REQUIRE(k_total == d->k_total, "ac_conv_tc: k_total %d != sum of taps*channels %d", d->k_total, k_total);
+    AC_REQUIRE(((uintptr_t)d->w & 15) == 0 && (k_total * 2) % 16 == 0, "ac_conv_tc: weights not 16-byte aligned");
+
+    // ---- choose (G, bk, stages) so that everything fits shared memory
+    const size_t fixed = 1024 /*align slack*/ + (2 * MAX_A_STAGES + 2 * MAX_W_STAGES + 5) * 8 + 16 + 64;
+    const long long m_tiles = (d->m_rows + TILE_M - 1) / TILE_M;
+    TcParams p{};
+    bool found = false;
+    const int sms = sm_count();
+    // pass 0 insists on deep rings (>= 3 A stages and >= 4 W stages, or resident weights); pass 1 takes anything that fits
+    for (int pass = 0; pass < 2 && !found; ++pass) {
+        for (int bk = d->bk; bk >= 16 && !found; bk >>= 1) {
+            bool ok = true;
+            for (int s = 0; s < n_ms; ++s) ok &= ms[s].hi->c0 % bk == 0;  // a k-block never straddles two phases
+            if (!ok) continue;
+            const int num_kb = k_total / bk;
+            const uint32_t w_kb_bytes = round_up((uint32_t)d->n_total * bk * 2, 1024);
+            const size_t w_res_total = (size_t)num_kb * w_kb_bytes * (1 + w_split);
+            const bool resident = n_tiles == 1 && n_tile == d->n_total && w_res_total <= 96 * 1024;
+            for (int G : {4, 2, 1}) {
+                if (d->g_hint > 0 && G != d->g_hint) continue;
+                if (d->g_hint <= 0 && G > 1) {
+                    if (G * n_tile * 2 > 512) continue;                                   // keep two accumulator stages when grouping
+                    if ((m_tiles / G) * n_tiles * d->batch < 2LL * sms) continue;         // not enough tiles to fill the chip
+                }
+                if (G * n_tile > 512) continue;
+                uint32_t a_plane = 0;  // A stage: the largest block over sources
+                for (int s = 0; s < n_ms; ++s) {
+                    const int R = G * TILE_M + (ms[s].hi->taps - 1) * ms[s].hi->dilation;
+                    const int pieces = (R + 255) / 256;
+                    const int box_rows = (int)round_up((R + pieces - 1) / pieces, 8);
+                    const uint32_t bytes = round_up((uint32_t)pieces * box_rows * bk * 2, 1024);
+                    if (bytes > a_plane) a_plane = bytes;
+                }
+                const uint32_t a_stage = a_plane * (any_lo ? 2 : 1);
+                const uint32_t w_plane = round_up((uint32_t)n_tile * bk * 2, 1024);
+                const uint32_t w_stage = w_plane * (1 + w_split);
+                const size_t budget = SMEM_LIMIT - fixed;
+                int a_stages, w_stages;
+                if (resident) {
+                    if (w_res_total + 2 * (size_t)a_stage > budget) continue;
+                    a_stages = (int)((budget - w_res_total) / a_stage);
+                    w_stages = 0;
+                } else {
+                    w_stages = 4;
+                    while (w_stages > 2 && (size_t)w_stages * w_stage + (pass == 0 ? 3 : 2) * (size_t)a_stage > budget) --w_stages;
+                    if ((size_t)w_stages * w_stage + 2 * (size_t)a_stage > budget) continue;
+                    a_stages = (int)((budget - (size_t)w_stages * w_stage) / a_stage);
+                    if (pass == 0 && (w_stages < 4 || a_stages < 3)) continue;
+                    if (a_stages > 4) {  // spare room: deepen the W ring first, it turns over `taps` times faster
+                        const int extra = (int)((budget - (size_t)w_stages * w_stage - 4 * (size_t)a_stage) / w_stage);
+                        w_stages = w_stages + extra > MAX_W_STAGES ? MAX_W_STAGES : w_stages + extra;
+                        a_stages = (int)((budget - (size_t)w_stages * w_stage) / a_stage);
+                    }
+                }
+                if (a_stages > MAX_A_STAGES) a_stages = MAX_A_STAGES;
+                if (a_stages < 2) continue;
+                p.G = G; p.bk = bk; p.num_kb = num_kb;
+                p.a_stages = a_stages; p.w_stages = w_stages;
+                p.a_stage_bytes = a_stage; p.a_plane_bytes = a_plane;
+                p.w_stage_bytes = w_stage; p.w_plane_bytes = w_plane;
+                p.w_kb_bytes = w_kb_bytes; p.w_res_plane = (uint32_t)((size_t)num_kb * w_kb_bytes);
+                p.w_resident = resident ? 1 : 0;
+                found = true;
+                break;
+            }
+        }
+    }
+    AC_REQUIRE(found, "ac_conv_tc: no tiling fits shared memory (n_total %d k_total %d)", d->n_total, k_total);
+    const int bk = p.bk;
+    p.w_split = w_split;
+    p.acc_stages = 2 * p.G * n_tile <= 512 ? 2 : 1;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.acc_stages * p.G * n_tile)) cols <<= 1;
+    p.tmem_cols = cols;
+
+    TcMaps maps;
+    p.n_src = n_ms;
+    int kcol = 0;
+    for (int s = 0; s < n_ms; ++s) {
+        const ac_tc_src& S = *ms[s].hi;
+        const int kper = S.c0 * S.phases;  // contraction length per tap
+        TcSrc& T = p.src[s];
+        T.c0 = S.c0; T.taps = S.taps; T.dil = S.dilation; T.shift = S.shift;
+        T.chunks = kper / bk;
+        T.kb0 = kcol / bk;
+        T.has_lo = ms[s].lo ? 1 : 0;
+        kcol += S.taps * kper;
+        const int R = p.G * TILE_M + (S.taps - 1) * S.dilation;
+        T.pieces = (R + 255) / 256;
+        T.box_rows = (int)round_up((R + T.pieces - 1) / T.pieces, 8);
+        for (int plane = 0; plane < 1 + T.has_lo; ++plane) {
+            const ac_tc_src& Q = plane ? *ms[s].lo : S;
+            cuuint64_t gdim[4] = {(cuuint64_t)Q.c0, (cuuint64_t)Q.phases, (cuuint64_t)Q.rows, (cuuint64_t)d->batch};
+            cuuint64_t gstr[3] = {(cuuint64_t)Q.phase_stride * 2, (cuuint64_t)Q.row_stride * 2, (cuuint64_t)Q.batch_stride * 2};
+            cuuint32_t box[4] = {(cuuint32_t)bk, 1, (cuuint32_t)T.box_rows, 1};
+            cuuint32_t est[4] = {1, 1, 1, 1};
+            CUresult r = encode(plane ? &maps.a_lo[s] : &maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Q.base),
+                                gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            AC_REQUIRE(r == CUDA_SUCCESS, "ac_conv_tc: cuTensorMapEncodeTiled(A%d) failed: %d", s, (int)r);
+        }
+        if (!T.has_lo) maps.a_lo[s] = maps.a[s];
+    }
+    for (int s = n_ms; s < MAX_SRC; ++s) { maps.a[s] = maps.a[0]; maps.a_lo[s] = maps.a[0]; }
     {
-        AC_REQUIRE(((uintptr_t)d->w & 15) == 0 && (k_total * 2) % 16 == 0, "ac_conv_tc: weights not 16-byte aligned");
         cuuint64_t gdim[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_total * (1 + w_split)};  // W_lo stacked under W_hi
         cuuint64_t gstr[1] = {(cuuint64_t)k_total * 2};
-        cuuint32_t box[2] = {(cuuint32_t)d->bk, (cuuint32_t)n_tile};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)n_tile};
         cuuint32_t est[2] = {1, 1};
-        CUresult r = encode(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, est,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(d->bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), gdim, gstr, box, est,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         AC_REQUIRE(r == CUDA_SUCCESS, "ac_conv_tc: cuTensorMapEncodeTiled(W) failed: %d", (int)r);
     }
 
-    p.a_stage_bytes = (uint32_t)((TILE_M * d->bk * 2 + 1023) & ~1023);
-    p.b_stage_bytes = (uint32_t)((n_tile * d->bk * 2 + 1023) & ~1023) * 2;  // room for the W_hi and W_lo tiles
-    const size_t fixed = 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16 + (size_t)d->n_total * 4 + 64;
-    int stages = (int)((200 * 1024 - fixed) / (p.a_stage_bytes + p.b_stage_bytes));
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages > p.num_kb * 2 && p.num_kb * 2 >= 2) stages = p.num_kb * 2;
-    AC_REQUIRE(stages >= 2, "ac_conv_tc: tile does not fit shared memory");
-    p.stages = stages;
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * n_tile)) cols <<= 1;
-    p.tmem_cols = cols;
+    p.w_rows = d->n_total;
+    p.n_total = d->n_total;
+    p.n_tile = n_tile;
+    p.n_tiles = n_tiles;
+    p.m_rows = d->m_rows;
+    p.m_groups = (d->m_rows + p.G * TILE_M - 1) / (p.G * TILE_M);
+    p.batch = d->batch;
     p.bias = d->bias; p.alpha = d->alpha;
     p.res = (const __nv_bfloat16*)d->res; p.y = (__nv_bfloat16*)d->y; p.y_act = (__nv_bfloat16*)d->y_act; p.y32 = d->y32;
     p.y_lo = (__nv_bfloat16*)d->y_lo; p.y_act_lo = (__nv_bfloat16*)d->y_act_lo;
@@ -423,17 +650,19 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     p.y_bs = d->y_bstride; p.ya_bs = d->y_act_bstride; p.y32_bs = d->y32_bstride; p.res_bs = d->res_bstride;
     p.out_shift = d->out_shift; p.out_valid = d->out_valid;
 
-    const size_t smem = fixed + (size_t)stages * (p.a_stage_bytes + p.b_stage_bytes);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    const size_t w_area = p.w_resident ? (size_t)p.w_res_plane * (1 + w_split) : (size_t)p.w_stages * p.w_stage_bytes;
+    const size_t smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + w_area;
+    AC_REQUIRE(smem <= (size_t)SMEM_LIMIT, "ac_conv_tc: shared memory %zu", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { ac::set_error("ac_conv_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        smem_set = 220 * 1024;
+        attr_set = true;
     }
-    const long long total_tiles = (long long)p.n_tiles * p.m_tiles * p.batch;
-    int grid = sm_count();
+    const long long total_tiles = (long long)p.n_tiles * p.m_groups * p.batch;
+    int grid = sms;
     if (d->grid_hint > 0) grid = d->grid_hint;
     if (total_tiles < grid) grid = (int)total_tiles;
-    conv_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(amap[0], amap[1], amap[2], amap[3], bmap, p);
+    conv_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     return ac::finish_launch("ac_conv_tc");
 }

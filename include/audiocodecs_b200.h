@@ -210,6 +210,7 @@ typedef struct ac_conv_tc_desc {
     int32_t n_tile_hint, grid_hint; /* 0 = automatic */
     const void* res_lo;          /* optional lo plane of `res` */
     const float* res32;          /* optional fp32 residual in the output's flat layout (clip stride res_bstride) */
+    int32_t g_hint;              /* 128-row sub-tiles per tile (1, 2 or 4) sharing one A block and one W block; 0 = automatic */
 } ac_conv_tc_desc;
 
 AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
