@@ -77,6 +77,7 @@ struct TcParams {
     float* y32;
     int w_rows;                   // rows of one weight plane in the W tensor map (n_total); W_lo starts at row w_rows
     int act, epi, act_mod;
+    int wide_ok;                  // every output/residual row run of 16 columns is 32-byte aligned: 256-bit stores
     long long y_bs, ya_bs, y32_bs, res_bs, out_shift, out_valid;
 };
 
@@ -108,6 +109,40 @@ __device__ __forceinline__ uint4 pack_lo(const float (&v)[8], const uint4& hi) {
     return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
+__device__ __forceinline__ void st_global_256(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                 "r"(g), "r"(h) : "memory");
+}
+
+__device__ __forceinline__ void add_bf16x16(float (&o)[16], const __nv_bfloat16* ptr) {
+    const uint4 r0 = reinterpret_cast<const uint4*>(ptr)[0], r1 = reinterpret_cast<const uint4*>(ptr)[1];
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+        o[2 * i] += __low2float(h2);
+        o[2 * i + 1] += __high2float(h2);
+    }
+}
+
+// 16 values -> one 32-byte store of the bf16 roundings (+ one of the rounding residuals when `lo` is given)
+__device__ __forceinline__ void store_bf16x16(const float (&o)[16], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    uint32_t q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = pack_bf16(o[2 * i], o[2 * i + 1]);
+    st_global_256(hi, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+    if (lo) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&q[i]);
+            r[i] = pack_bf16(o[2 * i] - __low2float(h2), o[2 * i + 1] - __high2float(h2));
+        }
+        st_global_256(lo, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+    }
+}
+
 __device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
     return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
 }
@@ -120,12 +155,14 @@ __device__ __forceinline__ float elu_ex2(float x) { return x > 0.f ? x : exp2f(x
 // (four per TMEM lane quarter) interleave over the (sub-tile, column chunk) items of the tile.
 template <int ACT>
 __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane,
-                                         int total_tiles) {
+                                         int total_tiles, const float* bias_s, const float* alpha_s, const float* ralpha_s) {
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int slot = (warp - FIRST_EPI_WARP) >> 2;   // 0..3
     const int chunks_n = p.n_tile / 16;
     const int items = p.G * chunks_n;
     const bool has_res = p.res != nullptr, has_res_lo = p.res_lo != nullptr, has_res32 = p.res32 != nullptr;
+    const bool periodic = p.act_mod < p.n_total;
+    const bool wide = p.wide_ok != 0;  // bias / alpha are indexed by n % act_mod (transposed conv: n = phase*C + c)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;
@@ -137,31 +174,98 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
         mbar_wait(&tfull[as], tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.G * p.n_tile;
+        int g = 0, c = slot;
+        while (c >= chunks_n) { c -= chunks_n; ++g; }
         for (int item = slot; item < items; item += EPI_WARPS / 4) {
-            const int g = item / chunks_n, c = item - g * chunks_n;
             uint32_t v[16];
             tmem_ld16(taddr + g * p.n_tile + c * 16, v);
             const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
             const int n0 = nt * p.n_tile + c * 16;
             const long long flat = (long long)m * p.n_total + n0 - p.out_shift;
             const bool ok = m < p.m_rows && n0 < p.n_total;
+            int ch0 = n0;  // channel of column n0
+            if (periodic) ch0 = n0 % p.act_mod;
+            c += EPI_WARPS / 4;
+            while (c >= chunks_n) { c -= chunks_n; ++g; }
             tmem_ld_wait();
             if (!ok) continue;
+            if (wide && flat >= 0 && flat + 16 <= p.out_valid && n0 + 16 <= p.n_total) {
+                // fast path: the lane's 16 columns are one aligned 32-byte (bf16) / 64-byte (fp32) run per output plane
+                float o[16];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int ch = ch0 + h * 8;
+                    if (ch >= p.act_mod) ch -= p.act_mod;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[h * 8 + i] = __uint_as_float(v[h * 8 + i]) + bb[i];
+                }
+                if (p.epi == AC_EPI_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = ac::gelu_erf(o[i]);
+                }
+                if (has_res) {
+                    add_bf16x16(o, p.res + (long long)b * p.res_bs + flat);
+                    if (has_res_lo) add_bf16x16(o, p.res_lo + (long long)b * p.res_bs + flat);
+                }
+                if (has_res32) {
+                    const float4* r = reinterpret_cast<const float4*>(p.res32 + (long long)b * p.res_bs + flat);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 rr = r[q];
+                        o[4 * q] += rr.x; o[4 * q + 1] += rr.y; o[4 * q + 2] += rr.z; o[4 * q + 3] += rr.w;
+                    }
+                }
+                if (p.y32) {
+                    float* d = p.y32 + (long long)b * p.y32_bs + flat;
+                    st_global_256(d, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                                  __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+                    st_global_256(d + 8, __float_as_uint(o[8]), __float_as_uint(o[9]), __float_as_uint(o[10]), __float_as_uint(o[11]),
+                                  __float_as_uint(o[12]), __float_as_uint(o[13]), __float_as_uint(o[14]), __float_as_uint(o[15]));
+                }
+                if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr);
+                if (p.y_act) {
+                    if (ACT == AC_ACT_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = elu_ex2(o[i]);
+                    } else if (ACT == AC_ACT_SNAKE) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            int ch = ch0 + h * 8;
+                            if (ch >= p.act_mod) ch -= p.act_mod;
+                            const float4 a0 = *reinterpret_cast<const float4*>(alpha_s + ch);
+                            const float4 a1 = *reinterpret_cast<const float4*>(alpha_s + ch + 4);
+                            const float4 r0 = *reinterpret_cast<const float4*>(ralpha_s + ch);
+                            const float4 r1 = *reinterpret_cast<const float4*>(ralpha_s + ch + 4);
+                            const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            const float ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float sn = __sinf(al[i] * o[h * 8 + i]);
+                                o[h * 8 + i] = fmaf(ra[i], sn * sn, o[h * 8 + i]);
+                            }
+                        }
+                    }
+                    store_bf16x16(o, p.y_act + (long long)b * p.ya_bs + flat, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + flat : nullptr);
+                }
+                continue;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {  // two 8-element vectors (16 B of bf16 each)
                 const long long f = flat + h * 8;
                 const int n = n0 + h * 8;
                 if (f < 0 || f >= p.out_valid || n >= p.n_total) continue;
+                int ch = ch0 + h * 8;
+                if (ch >= p.act_mod) ch -= p.act_mod;
                 float o[8];
-                if (p.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
                     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[h * 8 + i]) + bb[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[h * 8 + i]);
                 }
                 if (p.epi == AC_EPI_GELU) {
 #pragma unroll
@@ -193,15 +297,17 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a[i] = elu_ex2(o[i]);
                     } else if (ACT == AC_ACT_SNAKE) {
-                        // the channel of column n is n % act_mod; act_mod % 8 == 0 so a vector never wraps
-                        const float* ap = p.alpha + (n % p.act_mod);
-                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap));
-                        const float4 a1 = __ldg(reinterpret_cast<const float4*>(ap) + 1);
+                        // act_mod % 8 == 0, so a vector of 8 columns never wraps around the channel axis
+                        const float4 a0 = *reinterpret_cast<const float4*>(alpha_s + ch);
+                        const float4 a1 = *reinterpret_cast<const float4*>(alpha_s + ch + 4);
+                        const float4 r0 = *reinterpret_cast<const float4*>(ralpha_s + ch);
+                        const float4 r1 = *reinterpret_cast<const float4*>(ralpha_s + ch + 4);
                         const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const float ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float sn = __sinf(al[i] * o[i]);
-                            a[i] = fmaf(__frcp_rn(al[i] + 1e-9f), sn * sn, o[i]);
+                            a[i] = fmaf(ra[i], sn * sn, o[i]);
                         }
                     } else {
 #pragma unroll
@@ -314,6 +420,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint64_t* tempty = tfull + 2;
     uint64_t* wres_bar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(bars + 36);       // [act_mod]; 288 B into the (1024-aligned) barrier block
+    float* alpha_s = bias_s + p.act_mod;                       // [act_mod] snake only
+    float* ralpha_s = alpha_s + p.act_mod;                     // 1 / (alpha + 1e-9)
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
@@ -333,6 +442,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    for (int i = threadIdx.x; i < p.act_mod; i += THREADS) {
+        bias_s[i] = p.bias ? p.bias[i] : 0.f;
+        if (p.act == AC_ACT_SNAKE) {
+            const float a = p.alpha[i];
+            alpha_s[i] = a;
+            ralpha_s[i] = 1.0f / (a + 1e-9f);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -408,9 +525,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         else mma_role<1>(p, a_ring, w_area, a_full, a_empty, w_full, w_empty, tfull, tempty, wres_bar, tmem_base, total_tiles);
     } else {
         // ================================================================= epilogue (warps 3..18)
-        if (p.act == AC_ACT_ELU) epilogue<AC_ACT_ELU>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
-        else if (p.act == AC_ACT_SNAKE) epilogue<AC_ACT_SNAKE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
-        else epilogue<AC_ACT_NONE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles);
+        if (p.act == AC_ACT_ELU) epilogue<AC_ACT_ELU>(p, tmem_base, tfull, tempty, warp, lane, total_tiles, bias_s, alpha_s, ralpha_s);
+        else if (p.act == AC_ACT_SNAKE) epilogue<AC_ACT_SNAKE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles, bias_s, alpha_s, ralpha_s);
+        else epilogue<AC_ACT_NONE>(p, tmem_base, tfull, tempty, warp, lane, total_tiles, bias_s, alpha_s, ralpha_s);
     }
     tc_fence_before();
     __syncthreads();
@@ -521,8 +638,10 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     AC_REQUIRE(k_total == d->k_total, "ac_conv_tc: k_total %d != sum of taps*channels %d", d->k_total, k_total);
     AC_REQUIRE(((uintptr_t)d->w & 15) == 0 && (k_total * 2) % 16 == 0, "ac_conv_tc: weights not 16-byte aligned");
 
+    const int act_mod = d->act_mod > 0 ? d->act_mod : d->n_total;
+    AC_REQUIRE(act_mod % 8 == 0 && act_mod <= d->n_total && d->n_total % act_mod == 0, "ac_conv_tc: act_mod %d must divide n_total and be a multiple of 8", act_mod);
     // ---- choose (G, bk, stages) so that everything fits shared memory
-    const size_t fixed = 1024 /*align slack*/ + (2 * MAX_A_STAGES + 2 * MAX_W_STAGES + 5) * 8 + 16 + 64;
+    const size_t fixed = 1024 /*align slack*/ + 36 * 8 /*barriers + tmem slot*/ + (size_t)act_mod * 4 * (d->act == AC_ACT_SNAKE ? 3 : 1) + 64;
     const long long m_tiles = (d->m_rows + TILE_M - 1) / TILE_M;
     TcParams p{};
     bool found = false;
@@ -646,9 +765,16 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     p.y_lo = (__nv_bfloat16*)d->y_lo; p.y_act_lo = (__nv_bfloat16*)d->y_act_lo;
     p.res_lo = (const __nv_bfloat16*)d->res_lo; p.res32 = d->res32;
     AC_REQUIRE((!p.y_lo || p.y) && (!p.y_act_lo || p.y_act), "ac_conv_tc: lo plane without its hi plane");
-    p.act = d->act; p.epi = d->epi; p.act_mod = d->act_mod > 0 ? d->act_mod : d->n_total;
+    p.act = d->act; p.epi = d->epi; p.act_mod = act_mod;
     p.y_bs = d->y_bstride; p.ya_bs = d->y_act_bstride; p.y32_bs = d->y32_bstride; p.res_bs = d->res_bstride;
     p.out_shift = d->out_shift; p.out_valid = d->out_valid;
+    {
+        auto al = [](const void* ptr, size_t a) { return ((uintptr_t)ptr % a) == 0; };
+        const bool strides16 = d->n_total % 16 == 0 && d->out_shift % 16 == 0 && d->y_bstride % 16 == 0 && d->y_act_bstride % 16 == 0 &&
+                               d->y32_bstride % 16 == 0 && d->res_bstride % 16 == 0;
+        p.wide_ok = strides16 && al(d->y, 32) && al(d->y_lo, 32) && al(d->y_act, 32) && al(d->y_act_lo, 32) && al(d->y32, 32) &&
+                    al(d->res, 32) && al(d->res_lo, 32) && al(d->res32, 32);
+    }
 
     const size_t w_area = p.w_resident ? (size_t)p.w_res_plane * (1 + w_split) : (size_t)p.w_stages * p.w_stage_bytes;
     const size_t smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + w_area;

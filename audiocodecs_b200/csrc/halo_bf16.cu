@@ -24,7 +24,58 @@ __global__ void pad_halo_bf16_kernel(__nv_bfloat16* data, int rows, int ch, long
         base[(long long)pos * ch + c] = src >= 0 ? base[(long long)src * ch + c] : __float2bfloat16(0.f);
     }
 }
+
+// out = act(a + b) on split-bf16 tensors (hi [+lo] planes), 8 elements per thread.
+__global__ void add_act_bf16_kernel(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+                                    const __nv_bfloat16* b_lo, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, long long per_clip,
+                                    long long a_bs, long long b_bs, long long o_bs, int act) {
+    const int clip = blockIdx.y;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; e < per_clip; e += (long long)gridDim.x * blockDim.x * 8) {
+        float v[8];
+        auto acc = [&](const __nv_bfloat16* ptr, bool first) {
+            const uint4 r = *reinterpret_cast<const uint4*>(ptr);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h[i]);
+                v[2 * i] = first ? f.x : v[2 * i] + f.x;
+                v[2 * i + 1] = first ? f.y : v[2 * i + 1] + f.y;
+            }
+        };
+        acc(a_hi + clip * a_bs + e, true);
+        if (a_lo) acc(a_lo + clip * a_bs + e, false);
+        acc(b_hi + clip * b_bs + e, false);
+        if (b_lo) acc(b_lo + clip * b_bs + e, false);
+        if (act == AC_ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ac::elu_fast(v[i]);
+        }
+        __nv_bfloat162 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hi[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f = __bfloat1622float2(hi[i]);
+            lo[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        }
+        *reinterpret_cast<uint4*>(o_hi + clip * o_bs + e) = *reinterpret_cast<const uint4*>(hi);
+        if (o_lo) *reinterpret_cast<uint4*>(o_lo + clip * o_bs + e) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
 }  // namespace
+
+extern "C" int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
+                               int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,
+                               int32_t act, void* stream) {
+    AC_REQUIRE(a_hi && b_hi && out_hi && batch > 0 && batch <= 65535 && per_clip > 0 && per_clip % 8 == 0 && a_bstride % 8 == 0 &&
+                   b_bstride % 8 == 0 && out_bstride % 8 == 0, "ac_add_act_bf16: bad arguments");
+    AC_REQUIRE(act == AC_ACT_NONE || act == AC_ACT_ELU, "ac_add_act_bf16: act %d", act);
+    long long blocks = (per_clip / 8 + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    add_act_bf16_kernel<<<dim3((unsigned)blocks, batch), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo,
+        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, per_clip, a_bstride, b_bstride, out_bstride, act);
+    return ac::finish_launch("ac_add_act_bf16");
+}
 
 extern "C" int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
                                 int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream) {

@@ -113,7 +113,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
     uint64_t* d_full = bars + 3;      // accumulator of the current step complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int clip0 = cluster_id_x() * NBV;
@@ -145,25 +145,31 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                     tma_load_2d(a_s + kc * 16384 + g * 32 * 128, &wmap, w_full, kc * 64, g * HID + (int)rank * UPC);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(w_full, 0);
-            const uint32_t idesc = make_idesc_bf16(128, NB);
-            for (int t = 0; t < p.steps; ++t) {
-                const int par = t & 1;
-                if (t > 0) mbar_wait_cluster(&h_ready[par], ((t - 1) >> 1) & 1);  // h[t-1] complete in buffer `par`
-                tc_fence_after();
-                if (p.dbg && blockIdx.x == 0) { p.dbg[t * 8 + 5] = clock64(); }
-                const uint32_t a0 = smem_u32(a_s), b0 = smem_u32(b_s + par * B_BYTES);
+        // whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane
+        // issues the 32 tcgen05.mma of the step back to back
+        const bool leader = elect_one();
+        mbar_wait(w_full, 0);
+        const uint32_t idesc = make_idesc_bf16(128, NB);
+        const uint32_t a0 = smem_u32(a_s);
+        const uint64_t desc_base = make_smem_desc(0, 128);
+        for (int t = 0; t < p.steps; ++t) {
+            const int par = t & 1;
+            if (t > 0) mbar_wait_cluster(&h_ready[par], ((t - 1) >> 1) & 1);  // h[t-1] complete in buffer `par`
+            tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[t * 8 + 5] = clock64(); }
+            const uint32_t b0 = smem_u32(b_s + par * B_BYTES);
+            if (leader) {
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
-                    const uint64_t adesc = make_smem_desc(a0 + kc * 16384, 128);
-                    const uint64_t bdesc = make_smem_desc(b0 + kc * 2048, 128);
+                    const uint64_t adesc = desc_base | (((a0 + kc * 16384) & 0x3FFFFu) >> 4);
+                    const uint64_t bdesc = desc_base | (((b0 + kc * 2048) & 0x3FFFFu) >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
                 }
                 umma_commit(d_full);
-                if (p.dbg && blockIdx.x == 0) { p.dbg[t * 8 + 6] = clock64(); }
             }
+            __syncwarp();
+            if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[t * 8 + 6] = clock64(); }
         }
     } else {
         // ======================================================== epilogue: 128 threads

@@ -258,6 +258,18 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE,
         _PROFILER.end("lstm_tc_kernel", t0, 2.0 * B * T * C4 * (C4 // 4), 4.0 * pre.numel() + 2.0 * B * T * (C4 // 4))
 
 
+def add_act_bf16(a, b, out, act=ACT_NONE):
+    """out = act(a + b) on tc.Act tensors (valid rows only; hi [+lo] planes)."""
+    assert a.L == b.L == out.L and a.C == b.C == out.C and a.B == b.B == out.B
+    vp = lambda v: ctypes.c_void_p(v) if v is not None else None
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_add_act_bf16(vp(a.row_ptr(0)), vp(a.lo_ptr(0)), vp(b.row_ptr(0)), vp(b.lo_ptr(0)), vp(out.row_ptr(0)),
+                                          vp(out.lo_ptr(0)), a.B, a.L * a.C, a.bstride, b.bstride, out.bstride, act, _stream()),
+               "ac_add_act_bf16")
+    if _PROFILER:
+        _PROFILER.end("add_act_bf16", t0, 0.0, 6.0 * a.B * a.L * a.C)
+
+
 def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=None):
     """codes [B*N, Ktot] int64 -> bf16 rows of the tc.Act `out_act` ([B][hl+N+hr][D])."""
     _need_cuda(codes, codebooks)

@@ -224,6 +224,15 @@ AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch,
                             int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream);
 
 /*
+ * out = act(a + b) elementwise on split-bf16 activations (hi plane + optional lo plane each), `per_clip` elements per
+ * clip.  The skip-add + ELU that follows EnCodec's LSTM (HF/encodec:247 `hidden_states + residual`, then the next
+ * layer's ELU), kept out of the latency-bound recurrence kernel.
+ */
+AC_API int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
+                           int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,
+                           int32_t act, void* stream);
+
+/*
  * Edge layers of the bf16 pipeline (HBM-bound, SIMT):
  * first: y[b][t][c] = bias[c] + sum_j w[j][c] * x[b][pad(t + j - pad_left)]   (Cin = 1; fp32 waveform in, bf16 out:
  *        raw copy `y` and/or `y_act` = act(y), act = ELU or Snake(alpha));  C in {32, 64, 96}, K <= 8.
