@@ -121,6 +121,9 @@ class Encodec(Codec):
         cb = torch.stack([sd[f"quantizer.layers.{k}.codebook.embed"].float() for k in range(nq)]).contiguous()
         self.register_buffer("codebooks", cb, persistent=False)                 # [32, 1024, 128]
         self.register_buffer("cb_norm", cb.pow(2).sum(-1).contiguous(), persistent=False)  # |E|^2, HF/encodec:367
+        if self.precision == "bf16":  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
+            hi = cb.to(torch.bfloat16)
+            self.register_buffer("cb_split", torch.stack([hi, (cb - hi.float()).to(torch.bfloat16)]).contiguous(), persistent=False)
         self.register_buffer("_sync_ws", torch.zeros(64, dtype=torch.int32), persistent=False)
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
 
@@ -305,7 +308,10 @@ class Encodec(Codec):
         emb = enc(sig, self._vlen(sig, length))
         B, N, D = emb.shape
         toks = torch.empty((B, N, nq), device=sig.device, dtype=torch.int64)
-        ops.rvq_encode(emb.view(B * N, D), self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
+        if self.precision == "bf16":
+            ops.rvq_encode_tc(emb.view(B * N, D), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
+        else:
+            ops.rvq_encode(emb.view(B * N, D), self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
         return toks  # [B, N, K]
 
     def _sig_to_feats(self, sig, length):  # R/audiocodecs/encodec.py:97-117 (normalize=False: mask unused)

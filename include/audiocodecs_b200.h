@@ -126,6 +126,18 @@ typedef struct ac_lstm_tc_desc {
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
 
 /*
+ * Residual VQ encode on tcgen05 tensor cores (EnCodec metric, dim 128, n_codes a multiple of 256 up to 1024), all stages
+ * fused with the fp32 residual resident in shared memory.  Distance GEMM in error-compensated bf16
+ * (r_hi.E_hi + r_hi.E_lo + r_lo.E_hi, fp32 accumulate in TMEM), per-frame running top-2, exact fp32 re-score of the two
+ * candidates with the reference formula and tie rule, in-place subtract.  Same outputs as ac_rvq_encode_f32 (metric 0).
+ * cb_split_bf16: [2][stages_total][n_codes][dim] = bf16(E), bf16(E - bf16(E)); codebooks: the fp32 originals.
+ * Replaces HF/encodec/modeling_encodec.py:364-369,424-438.
+ */
+AC_API int ac_rvq_encode_tc(const float* x, const void* cb_split_bf16, const float* codebooks, const float* cb_norm,
+                            int64_t* codes_out, float* residual_out, int64_t rows, int32_t dim, int32_t n_codes,
+                            int32_t stages, int32_t stages_total, int32_t code_stride, int32_t code_offset, void* stream);
+
+/*
  * Residual VQ encode, all stages fused (fp32): for k < stages: idx = argmin_c ||r - E_k[c]||^2
  * (reference formula and tie rule: first index wins), r -= E_k[idx].
  *   metric 0: EnCodec  dist = -(|r|^2 - 2 r.E + |E|^2), argmax   (HF/encodec:364-369,424-438)

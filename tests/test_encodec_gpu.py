@@ -58,6 +58,33 @@ def test_rvq_encode_on_oracle_embeddings(encodec_sd, dev):
     assert tie < 0.02
 
 
+@pytest.mark.parametrize("B,T", [(3, 24000), (5, 31337), (1, 200)])
+def test_rvq_encode_tensor_core_on_oracle_embeddings(encodec_sd, dev, B, T):
+    """The tcgen05 RVQ kernel (split-bf16 distance GEMM + exact fp32 re-score of the top 2) fed the oracle's fp32
+    embeddings, all 32 stages: codes identical to the reference wherever its top-2 gap exceeds 1e-4; ragged tiles."""
+    from audiocodecs_b200 import ops
+    codec = _codec(encodec_sd, dev, num_codebooks=32, precision="bf16")
+    sig = make_input(17 + B, B, T)
+    with torch.no_grad():
+        emb = encodec_ref.encoder(encodec_sd, sig[:, None])
+        codes, gaps = encodec_ref.rvq_encode(encodec_sd, emb, 32, return_gaps=True)
+    x = emb.permute(0, 2, 1).contiguous().to(dev)  # [B,N,128]
+    B, N, D = x.shape
+    out = torch.full((B, N, 32), -1, device=dev, dtype=torch.int64)
+    res = torch.empty((B * N, D), device=dev, dtype=torch.float32)
+    ops.rvq_encode_tc(x.view(B * N, D), codec.cb_split, codec.codebooks, codec.cb_norm, out.view(B * N, 32), 32, residual_out=res)
+    m_safe, tie, m_all = code_report(out, codes.permute(1, 2, 0), gaps.permute(1, 2, 0))
+    assert m_safe == 1.0, (m_safe, tie, m_all)
+    # same decisions as the fp32 SIMT kernel, near-ties included (both re-score in fp32), and the same final residual
+    out2 = torch.empty_like(out)
+    res2 = torch.empty_like(res)
+    ops.rvq_encode(x.view(B * N, D), codec.codebooks, codec.cb_norm, out2.view(B * N, 32), 32, residual_out=res2)
+    agree = (out == out2).float().mean().item()
+    assert agree > 0.995, agree
+    same_rows = (out == out2).all(-1).view(-1)
+    assert torch.allclose(res[same_rows], res2[same_rows], atol=1e-6)
+
+
 def test_rvq_decode_bit_exact(encodec_sd, dev):
     codec = _codec(encodec_sd, dev, num_codebooks=32)
     toks = torch.randint(0, 1024, (2, 77, 32), generator=torch.Generator().manual_seed(1))
