@@ -105,6 +105,7 @@ def lib():
         L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]
         L.ac_add_act_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp]
+        L.ac_f32_to_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp]
         L.ac_pad_halo_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
         _lib = L
     return _lib

@@ -61,7 +61,38 @@ __global__ void add_act_bf16_kernel(const __nv_bfloat16* a_hi, const __nv_bfloat
         if (o_lo) *reinterpret_cast<uint4*>(o_lo + clip * o_bs + e) = *reinterpret_cast<const uint4*>(lo);
     }
 }
+
+// fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)), 8 elements per thread
+__global__ void f32_to_split_kernel(const float* x, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, long long per_clip, long long x_bs,
+                                    long long o_bs) {
+    const int clip = blockIdx.y;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; e < per_clip; e += (long long)gridDim.x * blockDim.x * 8) {
+        const float4 a = *reinterpret_cast<const float4*>(x + clip * x_bs + e);
+        const float4 b = *reinterpret_cast<const float4*>(x + clip * x_bs + e + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __nv_bfloat162 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hi[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f = __bfloat1622float2(hi[i]);
+            lo[i] = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        }
+        *reinterpret_cast<uint4*>(o_hi + clip * o_bs + e) = *reinterpret_cast<const uint4*>(hi);
+        if (o_lo) *reinterpret_cast<uint4*>(o_lo + clip * o_bs + e) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
 }  // namespace
+
+extern "C" int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, int32_t batch, int64_t per_clip, int64_t x_bstride,
+                                    int64_t out_bstride, void* stream) {
+    AC_REQUIRE(x && out_hi && batch > 0 && batch <= 65535 && per_clip > 0 && per_clip % 8 == 0 && x_bstride % 8 == 0 &&
+                   out_bstride % 8 == 0, "ac_f32_to_split_bf16: bad arguments");
+    long long blocks = (per_clip / 8 + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    f32_to_split_kernel<<<dim3((unsigned)blocks, batch), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                                                                                        per_clip, x_bstride, out_bstride);
+    return ac::finish_launch("ac_f32_to_split_bf16");
+}
 
 extern "C" int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
                                int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,

@@ -7,11 +7,22 @@ import math
 
 import torch
 
-from . import ops, packing
+from . import ops, packing, tc
 from .codec import Codec
 from .ops import ACT_NONE, ACT_SNAKE, EPI_NONE, EPI_TANH, PAD_ZERO, ConvSpec
+from .tc import Act, Src, TcWeights
 
 __all__ = ["DAC"]
+
+
+class TcAlpha:
+    """Snake alpha vector of one activation site (moves with the module like the packed weights)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def apply(self, fn):
+        self.t = fn(self.t)
 
 _ARCH = {  # descript-audio-codec 1.0.0 model zoo: tag -> (encoder rates, decoder rates, n_codebooks)
     "44khz": ((2, 4, 8, 8), (8, 8, 4, 2), 9),
@@ -25,15 +36,18 @@ class DAC(Codec):
     `state_dict` (transformers.DacModel key format, or descript's weight_g/weight_v format) and `precision`."""
 
     def __init__(self, sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False,
-                 state_dict=None, precision="fp32"):
+                 state_dict=None, precision="fp32", split_min_ch=512, split_res_min_ch=64):
         super().__init__(sample_rate, orig_sample_rate, mode)
-        if precision not in ("fp32",):
-            raise ValueError("DAC currently runs on the exact fp32 path only (precision='fp32')")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
+        # activated tensors (MMA operands) / raw residual-stream tensors with >= this many channels travel as (hi, lo) bf16 planes
+        self.split_min_ch = split_min_ch
+        self.split_res_min_ch = split_res_min_ch
         self.num_codebooks = num_codebooks
         self.vocab_size = 1024
         self.latent = latent
         self.precision = precision
-        self.compute_dtype = "f32"
+        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
         tag = f"{int(orig_sample_rate / 1000)}khz"  # R/audiocodecs/dac.py:55
         if tag not in _ARCH:
             raise ValueError(f"no DAC model for {tag}")
@@ -91,6 +105,9 @@ class DAC(Codec):
                     dec.append(self._res_unit(sd, f"{p}.res_unit{u}", d))
             dec.append(self._conv(sd, "decoder.conv2", padding=3, snake="decoder.snake1", epi=EPI_TANH))
             self._dec = dec
+        self._tcw = []
+        if self.precision == "bf16":
+            self._build_tc(sd)
         nq = sum(1 for k in sd if k.startswith("quantizer.quantizers.") and k.endswith(".codebook.weight"))
         q = "quantizer.quantizers.{}."
         stack = lambda f: torch.stack([f(q.format(k)) for k in range(nq)]).contiguous()
@@ -102,7 +119,122 @@ class DAC(Codec):
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
 
     def _packed(self):
-        return self._specs
+        return self._specs + self._tcw
+
+    # ------------------------------------------------------------------ bf16 tensor path: packing
+    def _tcw_conv(self, sd, prefix):
+        """Conv1d [Cout,Cin,K] -> [Cout][K*Cin] (column = tap*Cin + c; a stride-s / kernel-2s conv read through the
+        s-phase view has exactly this column order)."""
+        w = packing.fold_weight_norm(sd, prefix)
+        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"])
+        self._tcw.append(W)
+        return W
+
+    def _tcw_convtr(self, sd, prefix, stride):
+        w = packing.fold_weight_norm(sd, prefix)     # [Cin, Cout, 2s]
+        pk = packing.pack_convtr(w, stride)          # [2, Cin, s*Cout]
+        W = TcWeights(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride))
+        self._tcw.append(W)
+        return W
+
+    def _alpha(self, sd, name):
+        a = TcAlpha(sd[name + ".alpha"].float().reshape(-1).contiguous())
+        self._tcw.append(a)
+        return a
+
+    def _tc_units(self, sd, p):
+        return [(self._alpha(sd, f"{p}.res_unit{u}.snake1"), self._tcw_conv(sd, f"{p}.res_unit{u}.conv1"), d,
+                 self._alpha(sd, f"{p}.res_unit{u}.snake2"), self._tcw_conv(sd, f"{p}.res_unit{u}.conv2"))
+                for u, d in ((1, 1), (2, 3), (3, 9))]
+
+    def _build_tc(self, sd):
+        if self.mode != "decode":
+            self._tenc = []
+            for i, s in enumerate(self._enc_rates):
+                p = f"encoder.block.{i}"
+                self._tenc.append((self._tc_units(sd, p), self._alpha(sd, p + ".snake1"), self._tcw_conv(sd, p + ".conv1"), s))
+            self._tenc_last = (self._alpha(sd, "encoder.snake1"), self._tcw_conv(sd, "encoder.conv2"))
+        if self.mode != "encode":
+            self._tdec_first = self._tcw_conv(sd, "decoder.conv1")
+            self._tdec = []
+            for i, s in enumerate(self._dec_rates):
+                p = f"decoder.block.{i}"
+                self._tdec.append((self._alpha(sd, p + ".snake1"), self._tcw_convtr(sd, p + ".conv_t1", s), s, self._tc_units(sd, p)))
+            self._tdec_last_alpha = self._alpha(sd, "decoder.snake1")
+
+    # ------------------------------------------------------------------ bf16 tensor path: execution
+    def _split(self, C):
+        return C >= self.split_min_ch
+
+    def _split_res(self, C):
+        return C >= self.split_res_min_ch
+
+    def _tc_run_units(self, units, x, xs, next_alpha, out_halo=(0, 0)):
+        """three DacResidualUnits (HF/dac:173-207): x raw, xs = snake1(x) -> (y raw, ys = next_alpha-snake(y)).  The k7
+        conv reads its 7 dilated taps from ONE staged block of xs (zero padding = TMA out-of-bounds fill); the 1x1 conv
+        adds the residual and writes the raw stream plus the activation its consumer applies."""
+        B, L, C = x.B, x.L, x.C
+        dev = x.buf.device
+        for i, (a1, W7, d, a2, W1) in enumerate(units):
+            hs = Act(B, L, C, dev, split=self._split(C))
+            tc.conv_tc(W7, [Src(xs, taps=7, dilation=d, shift=-3 * d)], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
+            last = i == len(units) - 1
+            nxt = next_alpha if last else units[i + 1][0]
+            y = None if last else Act(B, L, C, dev, split=self._split_res(C))
+            hl, hr = out_halo if last else (0, 0)
+            ys = Act(B, L, C, dev, hl=hl, hr=hr, split=self._split(C))
+            tc.conv_tc(W1, [Src(hs)], L, res=x, y=None if last else y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
+            x, xs = y, ys
+        return xs
+
+    def _encoder_tc(self, sig):
+        B, T = sig.shape
+        dev = sig.device
+        C = self._enc[0].cout
+        x = Act(B, T, C, dev, split=False)   # the Cin=1 edge kernel writes single planes
+        xs = Act(B, T, C, dev, split=False)
+        ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xs, act=ACT_SNAKE, alpha=self._tenc[0][0][0][0].t)
+        L = T
+        for bi, (units, a_down, Wdown, s) in enumerate(self._tenc):
+            p = math.ceil(s / 2)
+            hr = -(p + L) % s
+            ys = self._tc_run_units(units, x, xs, a_down, out_halo=(p, hr))
+            ys.fill_halo(PAD_ZERO)
+            Lout = (L + 2 * p - 2 * s) // s + 1
+            C = 2 * C
+            nxt = self._tenc[bi + 1][0][0][0] if bi + 1 < len(self._tenc) else self._tenc_last[0]
+            last = bi + 1 == len(self._tenc)
+            x = None if last else Act(B, Lout, C, dev, split=self._split_res(C))
+            xs = Act(B, Lout, C, dev, split=self._split(C))
+            tc.conv_tc(Wdown, [Src(ys, taps=2, origin=-p, phases=s, rows=(p + L + hr) // s)], Lout, y=x, y_act=xs, act=ACT_SNAKE,
+                       alpha=nxt.t, name="down_tc")
+            L = Lout
+        z = torch.empty((B, L, C), device=dev, dtype=torch.float32)
+        tc.conv_tc(self._tenc_last[1], [Src(xs, taps=3, shift=-1)], L, y32=z, name="conv_k3_tc")
+        return z
+
+    def _decoder_tc(self, zq):
+        B, N, C = zq.shape
+        dev = zq.device
+        z = Act(B, N, C, dev, split=True)
+        ops.f32_to_act(zq.contiguous(), z)
+        C = self._tdec_first.n_total
+        xs = Act(B, N, C, dev, split=self._split(C))
+        tc.conv_tc(self._tdec_first, [Src(z, taps=7, shift=-3)], N, y_act=xs, act=ACT_SNAKE, alpha=self._tdec[0][0].t, name="conv_k7_tc")
+        L = N
+        for bi, (a_up, Wtr, s, units) in enumerate(self._tdec):
+            p = math.ceil(s / 2)
+            C = C // 2
+            Lout = L * s
+            x = Act(B, Lout, C, dev, split=self._split_res(C))
+            us = Act(B, Lout, C, dev, split=self._split(C))
+            # transposed conv (k = 2s, stride s, padding p): 2-tap GEMM over n = (phase, cout), flat output shifted by p*C
+            tc.conv_tc(Wtr, [Src(xs, taps=2, shift=-1)], L + 1, y=x, y_act=us, act=ACT_SNAKE, alpha=units[0][0].t, act_mod=C,
+                       out_rows=Lout, out_ch=C, out_shift=p * C, name="convtr_tc")
+            nxt = self._tdec[bi + 1][0] if bi + 1 < len(self._tdec) else self._tdec_last_alpha
+            xs = self._tc_run_units(units, x, us, nxt)
+            L = Lout
+        return ops.conv_last_bf16(self._dec[-1], xs, epi=EPI_TANH)
 
     # ------------------------------------------------------------------ pieces
     def _stack(self, layers, x):
@@ -122,19 +254,24 @@ class DAC(Codec):
         # post-projection embeddings: out_proj_k(codebook_k) -> [K, C, 1024]
         return torch.einsum("kcd,khd->kch", self.codebooks[:K], self.w_out[:K]) + self.b_out[:K, None, :]
 
+    def _encode_latents(self, sig):
+        if self.precision == "bf16":
+            return self._encoder_tc(sig.contiguous())
+        return self._stack(self._enc, sig.contiguous()[:, :, None])
+
     def _sig_to_toks(self, sig, length):  # R/audiocodecs/dac.py:94-100 (`length` is ignored by the reference)
-        z = self._stack(self._enc, sig.contiguous()[:, :, None])
+        z = self._encode_latents(sig)
         return ops.dac_rvq_encode(z, self.w_in, self.b_in, self.codebooks, self.w_out, self.b_out, self.num_codebooks)
 
     def _sig_to_feats(self, sig, length):  # R/audiocodecs/dac.py:103-112
-        z = self._stack(self._enc, sig.contiguous()[:, :, None])
+        z = self._encode_latents(sig)
         if self.latent:
             w = self.w_in[0].t().contiguous()[None]  # [1,1024,8]
             return ops.conv(ConvSpec(w, self.b_in[0], cout=8, geometry="same"), z)
         return z
 
     def _sig_to_qfeats(self, sig, length):  # R/audiocodecs/dac.py:115-121
-        z = self._stack(self._enc, sig.contiguous()[:, :, None])
+        z = self._encode_latents(sig)
         return ops.dac_rvq_encode(z, self.w_in, self.b_in, self.codebooks, self.w_out, self.b_out, self.num_codebooks,
                                   want_zq=True)[1]
 
@@ -143,4 +280,6 @@ class DAC(Codec):
         return ops.dac_rvq_decode(toks, self.codebooks[:K], self.w_out[:K], self.b_out[:K], err_flag=self._err)
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/dac.py:124-130
+        if self.precision == "bf16":
+            return self._decoder_tc(self._toks_to_qfeats(toks, length))
         return self._stack(self._dec, self._toks_to_qfeats(toks, length))[:, :, 0]

@@ -270,6 +270,18 @@ def add_act_bf16(a, b, out, act=ACT_NONE):
         _PROFILER.end("add_act_bf16", t0, 0.0, 6.0 * a.B * a.L * a.C)
 
 
+def f32_to_act(x, out):
+    """x [B, L, C] fp32 contiguous -> tc.Act `out` (hi [+lo] planes, valid rows)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (out.B, out.L, out.C)
+    vp = lambda v: ctypes.c_void_p(v) if v is not None else None
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_f32_to_split_bf16(_ptr(x), vp(out.row_ptr(0)), vp(out.lo_ptr(0)), out.B, out.L * out.C, x.stride(0),
+                                               out.bstride, _stream()), "ac_f32_to_split_bf16")
+    if _PROFILER:
+        _PROFILER.end("f32_to_split_bf16", t0, 0.0, 6.0 * x.numel())
+
+
 def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=None):
     """codes [B*N, Ktot] int64 -> bf16 rows of the tc.Act `out_act` ([B][hl+N+hr][D])."""
     _need_cuda(codes, codebooks)

@@ -244,6 +244,11 @@ AC_API int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi,
                            int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,
                            int32_t act, void* stream);
 
+/* fp32 [batch][per_clip] -> split-bf16 planes hi = bf16(x), lo = bf16(x - hi) (lo optional): the quantised latents
+ * (RVQ decode output, fp32) entering the tensor-core decoder. */
+AC_API int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, int32_t batch, int64_t per_clip, int64_t x_bstride,
+                                int64_t out_bstride, void* stream);
+
 /*
  * Edge layers of the bf16 pipeline (HBM-bound, SIMT):
  * first: y[b][t][c] = bias[c] + sum_j w[j][c] * x[b][pad(t + j - pad_left)]   (Cin = 1; fp32 waveform in, bf16 out:

@@ -10,11 +10,12 @@ from oracle import weights
 which = sys.argv[1] if len(sys.argv) > 1 else "encodec"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 secs = float(sys.argv[3]) if len(sys.argv) > 3 else 10.0
+smin = int(sys.argv[4]) if len(sys.argv) > 4 else 512
 dev = torch.device("cuda:0")
 if which == "encodec":
     codec, sr = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0)), 24000
 elif which == "dac":
-    codec, sr = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision="bf16"), 44100
+    codec, sr = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision="bf16", split_min_ch=smin), 44100
 else:
     codec, sr = A.Mimi(24000, num_codebooks=8, state_dict=weights.mimi_state_dict(0), precision="bf16"), 24000
 codec = codec.eval().to(dev)
