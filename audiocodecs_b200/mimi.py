@@ -8,13 +8,15 @@ import math
 
 import torch
 
-from . import ops, packing
+from . import ops, packing, tc
 from .codec import Codec
 from .ops import ACT_ELU, ACT_NONE, EPI_GELU, PAD_REPLICATE, PAD_ZERO, ConvSpec
+from .tc import Act, Src, TcWeights
 
 __all__ = ["Mimi"]
 
 RATIOS = (8, 6, 5, 4)  # MimiConfig().upsampling_ratios
+SPLIT_MIN_CH = 128     # activations with >= this many channels travel as (hi, lo) bf16 pairs (precision)
 HID, HEADS, HEAD_DIM, WINDOW, LAYERS = 512, 8, 64, 250, 8
 
 
@@ -24,13 +26,13 @@ class Mimi(Codec):
 
     def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32"):
         super().__init__(sample_rate, 24000, mode)
-        if precision not in ("fp32",):
-            raise ValueError("Mimi currently runs on the exact fp32 path only (precision='fp32')")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
         self.num_codebooks = num_codebooks
         self.vocab_size = 2048
         self.latent = latent
         self.precision = precision
-        self.compute_dtype = "f32"
+        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
         if state_dict is None:
             try:
                 from transformers import MimiModel
@@ -105,6 +107,9 @@ class Mimi(Codec):
                 idx += 3
             dec.append(self._conv(sd, f"decoder.layers.{idx}.conv", act=ACT_ELU))
             self._dec = dec
+        self._tcw = []
+        if self.precision == "bf16":
+            self._build_tc(sd)
         # quantizer: E = embed_sum / clamp(cluster_usage, 1e-5) (HF/mimi:1188-1195); semantic (1) then acoustic (31) codebooks
         cbs = []
         for which, n in (("semantic", 1), ("acoustic", 31)):
@@ -122,7 +127,121 @@ class Mimi(Codec):
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
 
     def _packed(self):
-        return self._specs
+        return self._specs + self._tcw
+
+    # ------------------------------------------------------------------ bf16 tensor path: packing
+    def _tw(self, w, bias=None):
+        W = TcWeights(w, bias)
+        self._tcw.append(W)
+        return W
+
+    def _tw_conv(self, sd, prefix):
+        w = packing.fold_weight_norm(sd, prefix)  # [Cout, Cin, K] -> [Cout][K*Cin], column = tap*Cin + c
+        return self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"])
+
+    def _tw_convtr(self, sd, prefix, stride):
+        pk = packing.pack_convtr(packing.fold_weight_norm(sd, prefix), stride)  # [2, Cin, s*Cout]
+        return self._tw(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride))
+
+    def _tw_transformer(self, sd, name):
+        out = []
+        for l in range(LAYERS):
+            p = f"{name}.layers.{l}."
+            qkv = torch.cat([sd[p + f"self_attn.{w}.weight"].float() for w in ("q_proj", "k_proj", "v_proj")], dim=0)
+            o = sd[p + "self_attn.o_proj.weight"].float() * sd[p + "self_attn_layer_scale.scale"].float().view(-1, 1)
+            fc2 = sd[p + "mlp.fc2.weight"].float() * sd[p + "mlp_layer_scale.scale"].float().view(-1, 1)
+            out.append((self._tw(qkv), self._tw(o), self._tw(sd[p + "mlp.fc1.weight"].float()), self._tw(fc2)))
+        return out
+
+    def _build_tc(self, sd):
+        if self.mode != "decode":
+            idx, self._tenc = 1, []
+            for r in reversed(RATIOS):
+                self._tenc.append((self._tw_conv(sd, f"encoder.layers.{idx}.block.1.conv"), self._tw_conv(sd, f"encoder.layers.{idx}.block.3.conv"),
+                                   self._tw_conv(sd, f"encoder.layers.{idx + 2}.conv"), r))
+                idx += 3
+            self._tenc_last = self._tw_conv(sd, f"encoder.layers.{idx + 1}.conv")
+            self._tenc_tr = self._tw_transformer(sd, "encoder_transformer")
+        if self.mode != "encode":
+            self._tdec_tr = self._tw_transformer(sd, "decoder_transformer")
+            self._tdec_first = self._tw_conv(sd, "decoder.layers.0.conv")
+            idx, self._tdec = 2, []
+            for r in RATIOS:
+                self._tdec.append((self._tw_convtr(sd, f"decoder.layers.{idx}.conv", r), self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.1.conv"),
+                                   self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.3.conv"), r))
+                idx += 3
+
+    # ------------------------------------------------------------------ bf16 tensor path: execution
+    def _tc_resblock(self, Wk3, Wk1, x, xe, ye):
+        """MimiResnetBlock (HF/mimi:412-451), identity shortcut, causal zero padding (TMA out-of-bounds fill):
+        x raw, xe = ELU(x) -> ye = ELU(x + conv_k1(ELU(conv_k3(xe))))."""
+        B, L, C = x.B, x.L, x.C
+        he = Act(B, L, C // 2, x.buf.device, split=C // 2 >= SPLIT_MIN_CH)
+        tc.conv_tc(Wk3, [Src(xe, taps=3, shift=-2)], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
+        tc.conv_tc(Wk1, [Src(he)], L, res=x, y_act=ye, act=ACT_ELU, name="res_k1_tc")
+
+    def _tc_transformer(self, layers, tws, h):
+        """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,
+        fp32 accumulate, residual added in fp32 in the epilogue); LayerNorm and the 250-token attention stay fp32 SIMT."""
+        B, T, C = h.shape
+        dev = h.device
+        xa = Act(B, T, C, dev, split=True)
+        fa = Act(B, T, 4 * C, dev, split=True)
+        qkv = torch.empty((B, T, 3 * C), device=dev, dtype=torch.float32)
+        for (ln, *_), (Wqkv, Wo, Wfc1, Wfc2) in zip(layers, tws):
+            ops.f32_to_act(ops.layernorm(h, getattr(self, ln[0]), getattr(self, ln[1])), xa)
+            tc.conv_tc(Wqkv, [Src(xa)], T, y32=qkv, name="tr_qkv_tc")
+            ops.f32_to_act(ops.attention(qkv, self.inv_freq, HEADS, HEAD_DIM, WINDOW), xa)
+            tc.conv_tc(Wo, [Src(xa)], T, res32=h, y32=h, name="tr_o_tc")
+            ops.f32_to_act(ops.layernorm(h, getattr(self, ln[2]), getattr(self, ln[3])), xa)
+            tc.conv_tc(Wfc1, [Src(xa)], T, y=fa, epi=EPI_GELU, name="tr_fc1_tc")
+            tc.conv_tc(Wfc2, [Src(fa)], T, res32=h, y32=h, name="tr_fc2_tc")
+        return h
+
+    def _encoder_tc(self, sig):
+        B, T = sig.shape
+        dev = sig.device
+        C = self._enc[0].cout
+        x = Act(B, T, C, dev)
+        xe = Act(B, T, C, dev)
+        ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU)
+        L = T
+        for i, (Wk3, Wk1, Wdown, r) in enumerate(self._tenc):
+            Lout = -(-L // r)
+            ye = Act(B, L, C, dev, hr=Lout * r - L, split=C >= SPLIT_MIN_CH)
+            self._tc_resblock(Wk3, Wk1, x, xe, ye)
+            ye.fill_halo(PAD_ZERO)
+            C = 2 * C
+            last = i == len(self._tenc) - 1
+            x = None if last else Act(B, Lout, C, dev, split=C >= SPLIT_MIN_CH)
+            xe = Act(B, Lout, C, dev, split=C >= SPLIT_MIN_CH)
+            # kernel 2r / stride r causal conv: 2 taps over the r-phase view, tap 0 = the previous view row (zero for row 0)
+            tc.conv_tc(Wdown, [Src(ye, taps=2, shift=-1, phases=r, rows=Lout)], Lout, y=x, y_act=xe, act=ACT_ELU, name="down_tc")
+            L = Lout
+        h = torch.empty((B, L, self._tenc_last.n_total), device=dev, dtype=torch.float32)
+        tc.conv_tc(self._tenc_last, [Src(xe, taps=3, shift=-2)], L, y32=h, name="conv_k3_tc")
+        return h
+
+    def _decoder_tc(self, z):
+        B, N, C = z.shape
+        dev = z.device
+        za = Act(B, N, C, dev, split=True)
+        ops.f32_to_act(z.contiguous(), za)
+        C = self._tdec_first.n_total
+        ye = Act(B, N, C, dev, split=True)
+        tc.conv_tc(self._tdec_first, [Src(za, taps=7, shift=-6)], N, y_act=ye, act=ACT_ELU, name="conv_k7_tc")
+        L = N
+        for Wtr, Wk3, Wk1, r in self._tdec:
+            C = C // 2
+            Lout = L * r
+            sp = C >= SPLIT_MIN_CH
+            x = Act(B, Lout, C, dev, split=sp)
+            xe = Act(B, Lout, C, dev, split=sp)
+            tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C, name="convtr_tc")
+            ye = Act(B, Lout, C, dev, split=sp)
+            self._tc_resblock(Wk3, Wk1, x, xe, ye)
+            L = Lout
+        return ops.conv_last_bf16(self._dec[-1], ye)
 
     # ------------------------------------------------------------------ pieces
     def _seanet(self, layers, x):
@@ -146,8 +265,11 @@ class Mimi(Codec):
 
     def _embeddings(self, sig):
         """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
-        x = self._seanet(self._enc, sig.contiguous()[:, :, None])
-        x = self._run_transformer(self._enc_tr, x)
+        if self.precision == "bf16":
+            x = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
+        else:
+            x = self._seanet(self._enc, sig.contiguous()[:, :, None])
+            x = self._run_transformer(self._enc_tr, x)
         return ops.conv(self._down, x)
 
     def _check_k(self, K):
@@ -200,5 +322,7 @@ class Mimi(Codec):
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/mimi.py:144-148 ; HF/mimi:1613-1631
         z = self._toks_to_qfeats(toks, length)
         z = ops.upsample_dw(z, self.up_w)
+        if self.precision == "bf16":
+            return self._decoder_tc(self._tc_transformer(self._dec_tr, self._tdec_tr, z))
         z = self._run_transformer(self._dec_tr, z)
         return self._seanet(self._dec, z)[:, :, 0]

@@ -24,6 +24,10 @@ SECONDS = 10
 WORKLOADS = {
     # name: (sample_rate, K, default per-GPU batch, algorithmic GFLOP per audio-second enc+dec -- SURVEY 8d)
     "encodec": dict(sr=24000, K=8, batch=64, gflop_per_s=6.12, desc="EnCodec-24k K=8 64x10s mono encode+decode"),
+    # the other BASELINE.json configs: extra bench lines on request (--codec), never the default
+    "encodec32": dict(sr=24000, K=32, batch=64, gflop_per_s=6.59, desc="EnCodec-24k K=32 64x10s mono encode+decode"),
+    "dac": dict(sr=44100, K=9, batch=64, gflop_per_s=199.8, desc="DAC-44.1k K=9 64x10s mono encode+decode"),
+    "mimi": dict(sr=24000, K=8, batch=128, gflop_per_s=11.0, desc="Mimi-24k K=8 128x10s mono encode+decode"),
 }
 
 
@@ -43,7 +47,25 @@ def load_peaks():
 
 def make_state_dict(codec):
     from oracle import weights  # deterministic random-init weights (no checkpoints offline); not on the timed path
-    return {"encodec": weights.encodec_state_dict}[codec](0)
+    return {"encodec": weights.encodec_state_dict, "encodec32": weights.encodec_state_dict, "dac": weights.dac_state_dict,
+            "mimi": weights.mimi_state_dict}[codec](0)
+
+
+def make_codec(codec, sd):
+    import audiocodecs_b200 as A
+    wl = WORKLOADS[codec]
+    if codec in ("encodec", "encodec32"):
+        return A.Encodec(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd)
+    if codec == "dac":
+        return A.DAC(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision="bf16")
+    return A.Mimi(wl["sr"], num_codebooks=wl["K"], state_dict=sd)
+
+
+def oracle_fns(codec):
+    """(sig_to_toks, toks_to_sig) of the CPU oracle for this codec (cpu_baseline / --impl reference legs only)."""
+    from oracle import dac_ref, encodec_ref, mimi_ref
+    mod = {"encodec": encodec_ref, "encodec32": encodec_ref, "dac": dac_ref, "mimi": mimi_ref}[codec]
+    return mod.sig_to_toks, mod.toks_to_sig
 
 
 class ClockSampler:
@@ -94,7 +116,6 @@ class ClockSampler:
 
 
 def run_ours(args, rank, world, local_rank):
-    import audiocodecs_b200 as A
     from audiocodecs_b200 import _lib, ops
 
     wl = WORKLOADS[args.codec]
@@ -102,11 +123,13 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     B, T = args.batch or wl["batch"], wl["sr"] * SECONDS
     sd = make_state_dict(args.codec)
-    codec = A.Encodec(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd).eval().to(dev)
+    codec = make_codec(args.codec, sd).eval().to(dev)
     g = torch.Generator().manual_seed(999 + rank)
     host_sig = (torch.randn(B, T, generator=g) * 0.1).pin_memory()
     sig = host_sig.to(dev)
-    host_out = torch.empty((B, T), dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        T_out = codec.toks_to_sig(codec.sig_to_toks(sig[:1])).shape[1]  # DAC returns 512*N samples, not T
+    host_out = torch.empty((B, T_out), dtype=torch.float32).pin_memory()
     audio_s_total = B * SECONDS * world
 
     def step():
@@ -194,18 +217,18 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "activations per step exceed the 126 MB L2 many times over (inputs_exceed_l2)",
                    "parallelism": f"clip-sharded x{world}, no data-path collective"},
         "e2e": {"value": round(e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": B * T * 4 * world,
-                "d2h_bytes_per_step": B * T * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "d2h_bytes_per_step": B * T_out * 4 * world, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args.codec, sd, clips=1, reps=3)
+        out["cpu_baseline"] = cpu_baseline(args.codec, sd, clips=1, reps=1 if args.codec == "dac" else 3)
     return out
 
 
 def cpu_baseline(codec, sd, clips, reps, threads=None):
     """The reference's CPU path (oracle port: the same ATen conv/LSTM/matmul ops the reference wrappers reach,
     fp32) on the host cores, on a bounded sample of the workload."""
-    from oracle import encodec_ref
+    enc, dec = oracle_fns(codec)
     wl = WORKLOADS[codec]
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -215,8 +238,9 @@ def cpu_baseline(codec, sd, clips, reps, threads=None):
     with torch.no_grad():
         for i in range(reps + 1):
             t0 = time.perf_counter()
-            toks = encodec_ref.sig_to_toks(sd, sig, wl["K"])
-            encodec_ref.toks_to_sig(sd, toks)
+            x = sig[:, :wl["sr"]] if (i == 0 and codec == "dac") else sig  # DAC: warm up on 1 s (a 10 s clip takes ~10 s)
+            toks = enc(sd, x, wl["K"])
+            dec(sd, toks)
             dt = time.perf_counter() - t0
             if i > 0:  # first rep is warm-up
                 best = dt if best is None else min(best, dt)
@@ -229,17 +253,17 @@ def run_reference(args, rank, world):
         return None
     wl = WORKLOADS[args.codec]
     sd = make_state_dict(args.codec)
-    clips = 2
+    clips = 1 if args.codec == "dac" else 2
     threads = os.cpu_count()
     torch.set_num_threads(threads)
-    from oracle import encodec_ref
+    enc, dec = oracle_fns(args.codec)
     g = torch.Generator().manual_seed(999)
     sig = torch.randn(clips, wl["sr"] * SECONDS, generator=g) * 0.1
 
     def step():
         with torch.no_grad():
-            toks = encodec_ref.sig_to_toks(sd, sig, wl["K"])
-            encodec_ref.toks_to_sig(sd, toks)
+            toks = enc(sd, sig, wl["K"])
+            dec(sd, toks)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step()
