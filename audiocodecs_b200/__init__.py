@@ -6,6 +6,7 @@ from .codec import Codec
 from .dac import DAC
 from .encodec import Encodec
 from .mimi import Mimi
+from . import shard  # noqa: F401  (clip sharding across GPUs)
 
 __version__ = "0.1.0"
 __all__ = ["Codec", "Encodec", "DAC", "Mimi"]
