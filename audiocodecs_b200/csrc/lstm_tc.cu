@@ -2,20 +2,22 @@
 // (ac_lstm_tc in include/audiocodecs_b200.h; replaces EncodecLSTM's nn.LSTM, HF/encodec:236-249).
 //
 // The 750-step chain is latency-bound, so everything a step needs stays on chip:
-//   * CTA r of the cluster owns hidden units [32r, 32r+32): its 128 gate rows (i,f,g,o x 32 units) of W_hh
-//     (bf16, 128 KB) are TMA-loaded once into shared memory as the A operand [128 x 512], K-major SW128.
-//   * h[t-1] of the cluster's 16 clips is the B operand [16 x 512] (bf16, 16 KB, double-buffered by step
-//     parity).  One step = 32 tcgen05.mma (M=128, N=16, K=16) into a 16-column TMEM accumulator:
-//     gates^T[128 gate rows][16 clips].
-//   * epilogue warp g (TMEM lane quarter g) holds gate g of 32 units: adds the hoisted input projection
-//     (pre, prefetched one step ahead), applies sigmoid/tanh, the four gates meet through shared memory,
-//     c stays in fp32 registers, h = o*tanh(c).
-//   * the CTA's new h slice (16 clips x 32 units) is written straight into the B buffers of all 16 CTAs
-//     (st.shared::cluster, distributed shared memory) and each CTA signals every peer's mbarrier with a
-//     cluster-scope release-arrive; the MMA thread of each CTA acquires it.  No global-memory round trip and
-//     no grid-wide barrier on the critical path.
+//   * CTA r of the cluster owns hidden units [32r, 32r+32): its 128 gate rows (i,f,g,o x 32 units) of W_hh (bf16,
+//     128 KB) live in TENSOR MEMORY for the whole kernel as the A operand of tcgen05.mma (lane = gate row, two bf16
+//     per 32-bit column: 256 of the 512 columns).  Streaming them from shared memory cost ~1000 cycles per step
+//     (128 KB at 128 B/clk); from TMEM the 32 MMAs of a step retire in a few hundred.
+//   * h[t-1] of the cluster's 16 clips is the B operand [16 x 512] (bf16, 16 KB, double-buffered by step parity) in
+//     the un-swizzled K-major core-matrix layout, chosen so that the 32 units a CTA produces are ONE contiguous
+//     1 KB run of every peer's operand.
+//   * epilogue warp g (TMEM lane quarter g) holds gate g of 32 units: adds the hoisted input projection (pre,
+//     prefetched one step ahead), applies sigmoid/tanh, the four gates meet through shared memory, c stays in fp32
+//     registers, h = o*tanh(c).
+//   * the CTA's new h slice is pushed to all 16 CTAs with 16 bulk async copies (cp.async.bulk shared::cta ->
+//     shared::cluster) that complete_tx on the DESTINATION's mbarrier: no per-thread remote stores, no cluster-scope
+//     release fence and no separate arrive on the critical path; the MMA warp of each CTA waits for 16 KB of
+//     transaction bytes.  (scripts/probe_tmem_a.cu pins the three hardware behaviours this relies on.)
 // Outputs (bf16 hi [+lo] planes for the next layer's GEMM, or act(h + skip) for the consumer conv) are
-// fire-and-forget global stores.
+// fire-and-forget global stores issued one step late, off the critical path.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -30,9 +32,13 @@ constexpr int HID = 512;      // hidden size (EnCodec)
 constexpr int UPC = HID / CL; // 32 units per CTA
 constexpr int NB = 16;        // clips per cluster (UMMA N)
 constexpr int THREADS = 192;
-constexpr uint32_t A_BYTES = 128 * HID * 2;         // 131072
 constexpr uint32_t B_BYTES = NB * HID * 2;          // 16384 per parity
+constexpr uint32_t SLICE_BYTES = NB * UPC * 2;      // 1024: one CTA's 32 units of all 16 clips
 constexpr uint32_t GS_FLOATS = 4 * UPC * 17;        // gate exchange, padded
+constexpr uint32_t TMEM_COLS = 512;                 // D: columns [0,16); W_hh slice: columns [256,512)
+constexpr uint32_t A_COL0 = 256;
+// un-swizzled K-major operand: 8x8 core matrices of 128 B; K-direction stride 256 B, N-direction (8-clip group) stride 128 B
+constexpr uint32_t B_KSTR = 256, B_NSTR = 128;
 
 struct LstmTcParams {
     const float* pre;            // [B][T][4*HID]
@@ -67,26 +73,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > (1u << 24)) __trap();
-    }
-}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
@@ -98,20 +84,41 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&w)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+        "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]), "r"(w[9]),
+          "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]),
+          "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]),
+          "r"(w[30]), "r"(w[31])
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_local, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_local), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+
 template <int NBV>  // clips handled per cluster (8 or 16); the UMMA N stays 16, unused B rows are zero
 __global__ void __launch_bounds__(THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_s = smem;                         // W_hh slice: 8 chunks of [128 rows][64] SW128 (16 KB each)
-    uint8_t* b_s = smem + A_BYTES;               // h operand: 2 parities x 8 chunks of [16 rows][64] SW128 (2 KB each)
-    float* gs = reinterpret_cast<float*>(b_s + 2 * B_BYTES);          // [4][32][17] activated gates
-    __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(gs + GS_FLOATS);  // [16 clips][32 units] new h slice
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + NB * UPC);
-    uint64_t* w_full = bars;          // W_hh landed
-    uint64_t* h_ready = bars + 1;     // [2] all 16 slices of h for this parity have arrived
-    uint64_t* d_full = bars + 3;      // accumulator of the current step complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint8_t* b_s = smem;                         // h operand: 2 parities x 16 KB, un-swizzled K-major core matrices
+    uint8_t* hs = b_s + 2 * B_BYTES;             // 2 x 1 KB: this CTA's new h slice, already in operand layout
+    float* gs = reinterpret_cast<float*>(hs + 2 * SLICE_BYTES);       // [4][32][17] activated gates
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gs + GS_FLOATS);
+    uint64_t* h_ready = bars;         // [2] 16 KB of h for this parity have landed (transaction bytes)
+    uint64_t* d_full = bars + 2;      // accumulator of the current step complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
@@ -119,63 +126,75 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
     const int clip0 = cluster_id_x() * NBV;
 
     if (threadIdx.x == 0) {
-        prefetch_tensormap(&wmap);
-        mbar_init(w_full, 1);
-        mbar_init(&h_ready[0], CL);
-        mbar_init(&h_ready[1], CL);
+        mbar_init(&h_ready[0], 1);
+        mbar_init(&h_ready[1], 1);
         mbar_init(d_full, 1);
         fence_barrier_init();
+        // h[0] (written by step 0) lands in parity 1, h[1] in parity 0: arm both before any peer can send
+        mbar_arrive_expect_tx(&h_ready[0], B_BYTES);
+        mbar_arrive_expect_tx(&h_ready[1], B_BYTES);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 32);
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     // h[-1] = 0: zero both parities of the B operand
     for (int i = threadIdx.x; i < (int)(2 * B_BYTES / 16); i += THREADS) reinterpret_cast<uint4*>(b_s)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_all();
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();  // every CTA's barriers are initialised before any peer signals them
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // W_hh rows of gate g, units [32 rank, +32): global row g*HID + 32*rank ; smem rows g*32.. of every k-chunk
-            mbar_arrive_expect_tx(w_full, A_BYTES);
-            for (int kc = 0; kc < 8; ++kc)
-                for (int g = 0; g < 4; ++g)
-                    tma_load_2d(a_s + kc * 16384 + g * 32 * 128, &wmap, w_full, kc * 64, g * HID + (int)rank * UPC);
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2) {
+        // W_hh slice -> TMEM: thread (gate g = lane quarter, unit u) owns global row g*HID + 32*rank + u (1 KB = 256 words)
+        const int g = warp & 3;
+        const uint4* src = reinterpret_cast<const uint4*>(w_hh + ((size_t)g * HID + rank * UPC + lane) * HID);
+        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + A_COL0;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t w[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 t = __ldg(src + c * 8 + q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+            tmem_st32(taddr + c * 32, w);
         }
-    } else if (warp == 1) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // every CTA's barriers are armed and operands zeroed before any peer sends
+    tc_fence_after();
+
+    if (warp == 1) {
         // whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane
         // issues the 32 tcgen05.mma of the step back to back
         const bool leader = elect_one();
-        mbar_wait(w_full, 0);
         const uint32_t idesc = make_idesc_bf16(128, NB);
-        const uint32_t a0 = smem_u32(a_s);
-        const uint64_t desc_base = make_smem_desc(0, 128);
+        uint64_t desc_base = 0;
+        desc_base |= (uint64_t)((B_KSTR >> 4) & 0x3FFF) << 16;  // leading byte offset = K-direction core-matrix stride
+        desc_base |= (uint64_t)((B_NSTR >> 4) & 0x3FFF) << 32;  // stride byte offset = 8-row group stride
+        desc_base |= 1ull << 46;
+        const uint32_t a_tmem = tmem_base + A_COL0;
         for (int t = 0; t < p.steps; ++t) {
             const int par = t & 1;
-            if (t > 0) mbar_wait_cluster(&h_ready[par], ((t - 1) >> 1) & 1);  // h[t-1] complete in buffer `par`
+            if (t > 0) {
+                mbar_wait(&h_ready[par], ((t - 1) >> 1) & 1);  // h[t-1]: 16 slices of 1 KB have landed in buffer `par`
+                if (leader && t + 2 < p.steps + 1) mbar_arrive_expect_tx(&h_ready[par], B_BYTES);  // re-arm for h[t+1]
+            }
             tc_fence_after();
             if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[t * 8 + 5] = clock64(); }
-            const uint32_t b0 = smem_u32(b_s + par * B_BYTES);
+            const uint64_t bdesc = desc_base | (((smem_u32(b_s) + par * B_BYTES) & 0x3FFFFu) >> 4);
             if (leader) {
 #pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    const uint64_t adesc = desc_base | (((a0 + kc * 16384) & 0x3FFFFu) >> 4);
-                    const uint64_t bdesc = desc_base | (((b0 + kc * 2048) & 0x3FFFFu) >> 4);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-                }
+                for (int ks = 0; ks < HID / 16; ++ks)  // K = 16 per MMA: 8 TMEM columns of A, two core matrices (512 B) of B
+                    umma_bf16_ts(tmem_base, a_tmem + ks * 8, bdesc + (uint64_t)((2 * B_KSTR) >> 4) * ks, idesc, ks != 0);
                 umma_commit(d_full);
             }
             __syncwarp();
             if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[t * 8 + 6] = clock64(); }
         }
-    } else {
+    } else if (warp >= 2) {
         // ======================================================== epilogue: 128 threads
         constexpr int CPT = NBV / 4;       // clips per thread in the cell update
-        constexpr int GROUPS = 128 / (NBV * 4);  // thread groups sharing the 16 destination CTAs of the broadcast
-        constexpr int DPT = CL / GROUPS;   // destinations per thread
         const int e = threadIdx.x - 64;
         const int g = warp & 3;            // TMEM lane quarter == gate index (rows g*32 + u)
         const int u = lane;
@@ -192,9 +211,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                 pre_next[b] = clip < p.batch ? __ldg(p.pre + ((size_t)clip * p.steps + t) * (4 * HID) + g * HID + gu) : 0.f;
             }
         };
-        // global outputs of step t are written one step late, while this thread would otherwise idle on the MMA:
-        // keeping them off the path between the DSMEM stores and the cluster-scope release (which waits for
-        // every earlier store of the thread) is worth ~2000 cycles per step.
+        // global outputs of step t are written one step late, while this thread would otherwise idle on the MMA
         auto emit = [&](int t) {
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
@@ -220,6 +237,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                 }
             }
         };
+        // destinations of this CTA's slice in every peer: operand buffer + 1 KB * rank, and the peer's h_ready barrier
+        const uint32_t dst_rank = (uint32_t)(lane & 15);
+        const uint32_t peer_b = map_to_cta(smem_u32(b_s) + rank * SLICE_BYTES, dst_rank);
+        const uint32_t peer_bar = map_to_cta(smem_u32(&h_ready[0]), dst_rank);
         load_pre(0);
         for (int t = 0; t < p.steps; ++t) {
             float pre_cur[NBV];
@@ -233,8 +254,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
             tc_fence_after();
             if (dbg) p.dbg[t * 8 + 1] = clock64();
             uint32_t v[NBV];
-            if constexpr (NBV == 16) tmem_ld16(tmem_d + ((uint32_t)(g * 32) << 16), v);
-            else tmem_ld8(tmem_d + ((uint32_t)(g * 32) << 16), v);
+            if constexpr (NBV == 16) tmem_ld16(tmem_base + ((uint32_t)(g * 32) << 16), v);
+            else tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16), v);
             tmem_ld_wait();
             tc_fence_before();
             if (g == 2) {  // warp-uniform: the g gate is tanh, i/f/o are sigmoids
@@ -246,6 +267,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
             }
             epi_bar_sync();
             if (dbg) p.dbg[t * 8 + 2] = clock64();
+            const int npar = (t + 1) & 1;
+            uint8_t* hsl = hs + npar * SLICE_BYTES;
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
                 const int b = bq * CPT + i;
@@ -253,27 +276,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
                 const float gg = gs[(2 * UPC + u) * 17 + b], og = gs[(3 * UPC + u) * 17 + b];
                 c_state[i] = fg * c_state[i] + ig * gg;
                 h_prev[i] = og * fast_tanh(c_state[i]);
-                hs[b * UPC + u] = __float2bfloat16(h_prev[i]);
+                // operand layout of the slice: core matrix (k_grp = u/8, n_grp = b/8), row b%8, element u%8
+                *reinterpret_cast<__nv_bfloat16*>(hsl + (u >> 3) * B_KSTR + (b >> 3) * B_NSTR + (b & 7) * 16 + (u & 7) * 2) =
+                    __float2bfloat16(h_prev[i]);
             }
             if (dbg) p.dbg[t * 8 + 3] = clock64();
             if (t + 1 < p.steps) {
-                epi_bar_sync();  // hs complete (and gs reads finished)
-                // broadcast the slice into parity (t+1)&1 of every CTA's B operand, in its swizzled K-major position
-                const int npar = (t + 1) & 1;
-                const int b = e / (4 * GROUPS);      // clip row
-                const int jj = (e / GROUPS) & 3;     // 16-byte unit of the 64-byte slice row
-                const int grp = e % GROUPS;
-                const uint4 val = *reinterpret_cast<const uint4*>(hs + b * UPC + jj * 8);
-                const int kc = (int)rank >> 1;
-                const int unit = 4 * ((int)rank & 1) + jj;
-                const uint32_t off = (uint32_t)(npar * B_BYTES + kc * 2048 + b * 128 + ((unit ^ (b & 7)) << 4));
-                const uint32_t local = smem_u32(b_s) + off;
-#pragma unroll
-                for (int d = 0; d < DPT; ++d) st_cluster_v4(map_to_cta(local, (uint32_t)(grp * DPT + d)), val);
-                fence_proxy_async_all();  // generic-proxy stores -> visible to the peers' async-proxy (tcgen05) reads
-                epi_bar_sync();
+                fence_proxy_async_all();  // this thread's generic-proxy stores to hs -> visible to the bulk-copy (async) proxy
+                epi_bar_sync();           // slice complete (and gs reads finished)
+                if (warp == 2 && lane < CL)
+                    bulk_copy_to_peer(peer_b + npar * B_BYTES, smem_u32(hsl), SLICE_BYTES, peer_bar + npar * 8);
                 if (dbg) p.dbg[t * 8 + 4] = clock64();
-                if (warp == 2 && lane < CL) mbar_arrive_remote_release(map_to_cta(smem_u32(&h_ready[npar]), (uint32_t)lane));
             }
         }
         emit(p.steps - 1);
@@ -284,13 +297,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap wmap, const LstmTcParams p) {
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_d, 32);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
 
@@ -299,26 +308,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     AC_REQUIRE(d->hidden == HID, "ac_lstm_tc: hidden %d (this kernel is built for %d)", d->hidden, HID);
     AC_REQUIRE(d->batch > 0 && d->steps > 0, "ac_lstm_tc: empty problem");
     AC_REQUIRE(d->out_hi || d->final_hi, "ac_lstm_tc: no output");
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    AC_REQUIRE(encode, "ac_lstm_tc: cuTensorMapEncodeTiled not available");
-    CUtensorMap wmap;
-    {
-        cuuint64_t gdim[2] = {HID, 4 * HID};
-        cuuint64_t gstr[1] = {HID * 2};
-        cuuint32_t box[2] = {64, UPC};
-        cuuint32_t est[2] = {1, 1};
-        CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w_hh_bf16), gdim, gstr, box, est,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        AC_REQUIRE(r == CUDA_SUCCESS, "ac_lstm_tc: cuTensorMapEncodeTiled failed: %d", (int)r);
-    }
-    const size_t smem = 1024 + A_BYTES + 2 * B_BYTES + GS_FLOATS * 4 + NB * UPC * 2 + 64;
+    const size_t smem = 1024 + 2 * B_BYTES + 2 * SLICE_BYTES + GS_FLOATS * 4 + 64;
     // Only 4 clusters of 16 CTAs are co-resident on a B200 (measured: 8 clusters ran as two waves), so a cluster
     // takes 16 clips unless the whole batch fits in 4 clusters of 8 (half the per-step epilogue work).
     const int nbv = d->batch <= 32 ? 8 : 16;
@@ -353,7 +343,8 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = nbv == 8 ? cudaLaunchKernelEx(&cfg, lstm_tc_kernel<8>, wmap, p) : cudaLaunchKernelEx(&cfg, lstm_tc_kernel<16>, wmap, p);
+    cudaError_t e = nbv == 8 ? cudaLaunchKernelEx(&cfg, lstm_tc_kernel<8>, (const __nv_bfloat16*)d->w_hh_bf16, p)
+                              : cudaLaunchKernelEx(&cfg, lstm_tc_kernel<16>, (const __nv_bfloat16*)d->w_hh_bf16, p);
     ac::count_launch();
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;

@@ -58,7 +58,7 @@ def make_codec(codec, sd):
         return A.Encodec(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd)
     if codec == "dac":
         return A.DAC(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision="bf16")
-    return A.Mimi(wl["sr"], num_codebooks=wl["K"], state_dict=sd)
+    return A.Mimi(wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision="bf16")
 
 
 def oracle_fns(codec):
