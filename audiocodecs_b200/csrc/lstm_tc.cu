@@ -31,7 +31,8 @@ constexpr int CL = 16;        // CTAs per cluster
 constexpr int HID = 512;      // hidden size (EnCodec)
 constexpr int UPC = HID / CL; // 32 units per CTA
 constexpr int NB = 16;        // clips per cluster (UMMA N)
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;   // two per TMEM lane quarter: each takes 8 of the 16 clips
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t B_BYTES = NB * HID * 2;          // 16384 per parity
 constexpr uint32_t SLICE_BYTES = NB * UPC * 2;      // 1024: one CTA's 32 units of all 16 clips
 constexpr uint32_t GS_FLOATS = 4 * UPC * 17;        // gate exchange, padded
@@ -74,7 +75,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
     return r;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -107,7 +108,6 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                  ::"r"(dst_cluster), "r"(src_local), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 
-template <int NBV>  // clips handled per cluster (8 or 16); the UMMA N stays 16, unused B rows are zero
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -123,7 +123,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int clip0 = cluster_id_x() * NBV;
+    const int clip0 = cluster_id_x() * NB;
 
     if (threadIdx.x == 0) {
         mbar_init(&h_ready[0], 1);
@@ -142,7 +142,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         // W_hh slice -> TMEM: thread (gate g = lane quarter, unit u) owns global row g*HID + 32*rank + u (1 KB = 256 words)
         const int g = warp & 3;
         const uint4* src = reinterpret_cast<const uint4*>(w_hh + ((size_t)g * HID + rank * UPC + lane) * HID);
@@ -193,21 +193,23 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             if (p.dbg && blockIdx.x == 0 && leader) { p.dbg[t * 8 + 6] = clock64(); }
         }
     } else if (warp >= 2) {
-        // ======================================================== epilogue: 128 threads
-        constexpr int CPT = NBV / 4;       // clips per thread in the cell update
-        const int e = threadIdx.x - 64;
+        // ======================================================== epilogue: 256 threads
+        constexpr int HC = NB / 2;         // clips per thread in the activation phase (this warp's half of the columns)
+        constexpr int CPT = NB / EPI_WARPS;  // clips per thread in the cell update
+        const int ew = warp - 2;           // 0..7
         const int g = warp & 3;            // TMEM lane quarter == gate index (rows g*32 + u)
+        const int ch = ew >> 2;            // which 8 clips this warp activates
         const int u = lane;
-        const int bq = e >> 5;             // clips bq*CPT .. for the cell update
         const int gu = (int)rank * UPC + u;
+        const bool dbg = p.dbg && blockIdx.x == 0 && threadIdx.x == 64;
         float c_state[CPT], h_prev[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) { c_state[i] = 0.f; h_prev[i] = 0.f; }
-        float pre_next[NBV];
+        float pre_next[HC];
         auto load_pre = [&](int t) {
 #pragma unroll
-            for (int b = 0; b < NBV; ++b) {
-                const int clip = clip0 + b;
+            for (int b = 0; b < HC; ++b) {
+                const int clip = clip0 + ch * HC + b;
                 pre_next[b] = clip < p.batch ? __ldg(p.pre + ((size_t)clip * p.steps + t) * (4 * HID) + g * HID + gu) : 0.f;
             }
         };
@@ -215,7 +217,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         auto emit = [&](int t) {
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                const int clip = clip0 + bq * CPT + i;
+                const int clip = clip0 + ew * CPT + i;
                 if (clip >= p.batch) continue;
                 const float h = h_prev[i];
                 const __nv_bfloat16 hb = __float2bfloat16(h);
@@ -237,33 +239,32 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
                 }
             }
         };
-        // destinations of this CTA's slice in every peer: operand buffer + 1 KB * rank, and the peer's h_ready barrier
-        const uint32_t dst_rank = (uint32_t)(lane & 15);
+        // destinations of this CTA's slice: every warp pushes to two peers (operand buffer + 1 KB * rank, and the peer's
+        // h_ready barrier); spreading the 16 bulk copies over the warps keeps each warp's issue loop short
+        const uint32_t dst_rank = (uint32_t)(ew * 2 + (lane & 1));
         const uint32_t peer_b = map_to_cta(smem_u32(b_s) + rank * SLICE_BYTES, dst_rank);
         const uint32_t peer_bar = map_to_cta(smem_u32(&h_ready[0]), dst_rank);
         load_pre(0);
         for (int t = 0; t < p.steps; ++t) {
-            float pre_cur[NBV];
+            float pre_cur[HC];
 #pragma unroll
-            for (int b = 0; b < NBV; ++b) pre_cur[b] = pre_next[b];
+            for (int b = 0; b < HC; ++b) pre_cur[b] = pre_next[b];
             if (t + 1 < p.steps) load_pre(t + 1);  // in flight during this step's MMA
             if (t > 0) emit(t - 1);
-            const bool dbg = p.dbg && blockIdx.x == 0 && e == 0;
             if (dbg) p.dbg[t * 8 + 0] = clock64();
             mbar_wait(d_full, t & 1);
             tc_fence_after();
             if (dbg) p.dbg[t * 8 + 1] = clock64();
-            uint32_t v[NBV];
-            if constexpr (NBV == 16) tmem_ld16(tmem_base + ((uint32_t)(g * 32) << 16), v);
-            else tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16), v);
+            uint32_t v[HC];
+            tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16) + ch * HC, v);
             tmem_ld_wait();
             tc_fence_before();
             if (g == 2) {  // warp-uniform: the g gate is tanh, i/f/o are sigmoids
 #pragma unroll
-                for (int b = 0; b < NBV; ++b) gs[(g * UPC + u) * 17 + b] = fast_tanh(__uint_as_float(v[b]) + pre_cur[b]);
+                for (int b = 0; b < HC; ++b) gs[(g * UPC + u) * 17 + ch * HC + b] = fast_tanh(__uint_as_float(v[b]) + pre_cur[b]);
             } else {
 #pragma unroll
-                for (int b = 0; b < NBV; ++b) gs[(g * UPC + u) * 17 + b] = fast_sigmoid(__uint_as_float(v[b]) + pre_cur[b]);
+                for (int b = 0; b < HC; ++b) gs[(g * UPC + u) * 17 + ch * HC + b] = fast_sigmoid(__uint_as_float(v[b]) + pre_cur[b]);
             }
             epi_bar_sync();
             if (dbg) p.dbg[t * 8 + 2] = clock64();
@@ -271,7 +272,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             uint8_t* hsl = hs + npar * SLICE_BYTES;
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                const int b = bq * CPT + i;
+                const int b = ew * CPT + i;
                 const float ig = gs[(0 * UPC + u) * 17 + b], fg = gs[(1 * UPC + u) * 17 + b];
                 const float gg = gs[(2 * UPC + u) * 17 + b], og = gs[(3 * UPC + u) * 17 + b];
                 c_state[i] = fg * c_state[i] + ig * gg;
@@ -282,10 +283,10 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             }
             if (dbg) p.dbg[t * 8 + 3] = clock64();
             if (t + 1 < p.steps) {
-                fence_proxy_async_all();  // this thread's generic-proxy stores to hs -> visible to the bulk-copy (async) proxy
+                fence_proxy_async();      // this thread's generic-proxy stores to hs (shared::cta only: a full proxy fence would also
+                                          // wait for the deferred global stores) -> visible to the bulk-copy (async) proxy
                 epi_bar_sync();           // slice complete (and gs reads finished)
-                if (warp == 2 && lane < CL)
-                    bulk_copy_to_peer(peer_b + npar * B_BYTES, smem_u32(hsl), SLICE_BYTES, peer_bar + npar * 8);
+                if (lane < 2) bulk_copy_to_peer(peer_b + npar * B_BYTES, smem_u32(hsl), SLICE_BYTES, peer_bar + npar * 8);
                 if (dbg) p.dbg[t * 8 + 4] = clock64();
             }
         }
@@ -308,13 +309,16 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     AC_REQUIRE(d->hidden == HID, "ac_lstm_tc: hidden %d (this kernel is built for %d)", d->hidden, HID);
     AC_REQUIRE(d->batch > 0 && d->steps > 0, "ac_lstm_tc: empty problem");
     AC_REQUIRE(d->out_hi || d->final_hi, "ac_lstm_tc: no output");
-    const size_t smem = 1024 + 2 * B_BYTES + 2 * SLICE_BYTES + GS_FLOATS * 4 + 64;
-    // Only 4 clusters of 16 CTAs are co-resident on a B200 (measured: 8 clusters ran as two waves), so a cluster
-    // takes 16 clips unless the whole batch fits in 4 clusters of 8 (half the per-step epilogue work).
-    const int nbv = d->batch <= 32 ? 8 : 16;
+    // The kernel needs ~42 KB of shared memory, but every CTA allocates all 512 TMEM columns: two CTAs of different
+    // clusters on one SM would block each other's tcgen05.alloc (cross-cluster deadlock), so the launch asks for more
+    // than half an SM's shared memory and exactly one CTA fits per SM.  Only 4 clusters of 16 CTAs are co-resident on a
+    // B200 (measured: 8 clusters ran as two waves), so a cluster takes 16 clips.
+    const size_t smem_used = 1024 + 2 * B_BYTES + 2 * SLICE_BYTES + GS_FLOATS * 4 + 64;
+    const size_t smem = smem_used > 120 * 1024 ? smem_used : 120 * 1024;
+    const int nbv = NB;
     static bool configured = false;
     if (!configured) {
-        for (const void* fn : {(const void*)lstm_tc_kernel<8>, (const void*)lstm_tc_kernel<16>}) {
+        for (const void* fn : {(const void*)lstm_tc_kernel}) {
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: func attributes: %s", cudaGetErrorString(e)); return (int)e; }
@@ -343,8 +347,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = nbv == 8 ? cudaLaunchKernelEx(&cfg, lstm_tc_kernel<8>, (const __nv_bfloat16*)d->w_hh_bf16, p)
-                              : cudaLaunchKernelEx(&cfg, lstm_tc_kernel<16>, (const __nv_bfloat16*)d->w_hh_bf16, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_kernel, (const __nv_bfloat16*)d->w_hh_bf16, p);
     ac::count_launch();
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
