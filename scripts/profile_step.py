@@ -1,5 +1,5 @@
-"""Two full-size steps (EnCodec-24k, 64 x 10 s, encode+decode) for ncu: step 1 warms up, step 2 is the profiled one.
-Usage under ncu: see profiles/README.md."""
+"""Two full-size steps for ncu: step 1 warms up, step 2 is the profiled one.
+Usage under ncu: python scripts/profile_step.py [steps] [encodec|dac|mimi] [batch]   (see profiles/README.md)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,9 +7,17 @@ import audiocodecs_b200 as A
 from oracle import weights
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+which = sys.argv[2] if len(sys.argv) > 2 else "encodec"
 dev = torch.device("cuda:0")
-codec = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0)).eval().to(dev)
-sig = (torch.randn(64, 240000, generator=torch.Generator().manual_seed(999)) * 0.1).to(dev)
+if which == "encodec":
+    codec, sr, B = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0)), 24000, 64
+elif which == "dac":
+    codec, sr, B = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision="bf16"), 44100, 64
+else:
+    codec, sr, B = A.Mimi(24000, num_codebooks=8, state_dict=weights.mimi_state_dict(0), precision="bf16"), 24000, 128
+B = int(sys.argv[3]) if len(sys.argv) > 3 else B
+codec = codec.eval().to(dev)
+sig = (torch.randn(B, sr * 10, generator=torch.Generator().manual_seed(999)) * 0.1).to(dev)
 for _ in range(steps):
     rec = codec.toks_to_sig(codec.sig_to_toks(sig))
 torch.cuda.synchronize()
