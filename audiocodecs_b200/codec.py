@@ -14,6 +14,10 @@ __all__ = ["Codec"]
 
 class Codec(torch.nn.Module, ABC):
     _MODES = ["encode", "decode", "reconstruct"]
+    # Activations of one call stay resident in HBM; a batch larger than this many audio samples (clips x samples at the
+    # codec rate) is processed in sub-batches so that any batch size fits the 180 GB of a B200 (the clips are
+    # independent, so chunking changes nothing but peak memory).  Sub-classes set it from their per-sample footprint.
+    max_chunk_samples = 256 * 240000
 
     def __init__(self, sample_rate, orig_sample_rate, mode="reconstruct"):
         super().__init__()
@@ -38,10 +42,20 @@ class Codec(torch.nn.Module, ABC):
         # hooks without spending kernels on an all-true padding mask
         return sig, length
 
+    def _chunks(self, n_clips, samples_per_clip):
+        per = max(1, int(self.max_chunk_samples // max(1, samples_per_clip)))
+        return [(a, min(n_clips, a + per)) for a in range(0, n_clips, per)]
+
+    def _chunked(self, fn, x, length, samples_per_clip):
+        spans = self._chunks(x.shape[0], samples_per_clip)
+        if len(spans) <= 1:
+            return fn(x, length)
+        return torch.cat([fn(x[a:b], None if length is None else length[a:b]) for a, b in spans], dim=0)
+
     @torch.no_grad()
     def sig_to_toks(self, sig, length=None):  # R/codec.py:57-66
         sig, length = self._prep_sig(sig, length)
-        return self._sig_to_toks(sig, length)
+        return self._chunked(self._sig_to_toks, sig, length, sig.shape[-1])
 
     @torch.no_grad()
     def sig_to_feats(self, sig, length=None):  # R/codec.py:68-77
@@ -55,8 +69,12 @@ class Codec(torch.nn.Module, ABC):
 
     @torch.no_grad()
     def toks_to_sig(self, toks, length=None):  # R/codec.py:90-100
-        sig = self._toks_to_sig(toks, length)
+        sig = self._chunked(self._toks_to_sig, toks, length, toks.shape[1] * self._hop())
         return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
+
+    def _hop(self):
+        """codec-rate samples per token frame (used only to size sub-batches)"""
+        return 320
 
     @torch.no_grad()
     def toks_to_qfeats(self, toks, length=None):  # R/codec.py:102-108

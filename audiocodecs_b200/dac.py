@@ -35,6 +35,11 @@ class DAC(Codec):
     """`DAC(sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False)`; extra keywords
     `state_dict` (transformers.DacModel key format, or descript's weight_g/weight_v format) and `precision`."""
 
+    max_chunk_samples = 64 * 441000  # ~0.2 KB of live activations per sample on the tensor path
+
+    def _hop(self):
+        return 512
+
     def __init__(self, sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False,
                  state_dict=None, precision="fp32", split_min_ch=512, split_res_min_ch=64):
         super().__init__(sample_rate, orig_sample_rate, mode)

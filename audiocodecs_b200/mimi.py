@@ -24,6 +24,9 @@ class Mimi(Codec):
     """`Mimi(sample_rate, mode="reconstruct", num_codebooks=8, latent=True)`; extra keywords `state_dict`
     (`transformers.MimiModel` key format; default: fetch kyutai/mimi like the reference, mimi.py:45) and `precision`."""
 
+    def _hop(self):
+        return 1920
+
     def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32"):
         super().__init__(sample_rate, 24000, mode)
         if precision not in ("fp32", "bf16"):

@@ -148,3 +148,15 @@ def test_full_size_roundtrip_properties(encodec_sd, dev):
     m_safe, tie, m_all = code_report(toks[5:6], ref_toks, gaps)
     assert m_safe >= 0.999, (m_safe, tie, m_all)
     assert (rec[5:6].cpu() - ref_rec).abs().max().item() <= WAVE_MAX_ABS_FP32
+
+
+def test_sub_batch_chunking_is_invisible(encodec_sd, dev):
+    """a batch larger than `max_chunk_samples` is processed in sub-batches: identical tokens and waveforms"""
+    codec = _codec(encodec_sd, dev, num_codebooks=8, precision="bf16")
+    sig = make_input(21, 7, 6400).to(dev)
+    toks = codec.sig_to_toks(sig)
+    rec = codec.toks_to_sig(toks)
+    codec.max_chunk_samples = 3 * 6400  # 3 clips per sub-batch -> chunks of 3, 3, 1
+    toks2 = codec.sig_to_toks(sig)
+    rec2 = codec.toks_to_sig(toks)
+    assert torch.equal(toks, toks2) and torch.equal(rec, rec2)
