@@ -48,6 +48,18 @@ class AcConvTcDesc(ctypes.Structure):
                 ("res_lo", c_vp), ("res32", c_vp), ("g_hint", c_i32)]
 
 
+class AcResunitTcDesc(ctypes.Structure):
+    """mirror of `struct ac_resunit_tc_desc`"""
+    _fields_ = [("a", c_vp), ("a_lo", c_vp), ("a_row_stride", c_i64), ("a_bstride", c_i64),
+                ("a_rows", c_i32), ("cin", c_i32), ("taps", c_i32), ("dilation", c_i32), ("shift", c_i32),
+                ("x", c_vp), ("x_lo", c_vp), ("x_bstride", c_i64), ("w1", c_vp), ("w2", c_vp),
+                ("w1_split", c_i32), ("w2_split", c_i32), ("ch", c_i32), ("cout", c_i32), ("h_split", c_i32),
+                ("bias1", c_vp), ("alpha1", c_vp), ("bias2", c_vp), ("alpha2", c_vp), ("act1", c_i32), ("act2", c_i32),
+                ("res", c_vp), ("res_lo", c_vp), ("res_bstride", c_i64),
+                ("y", c_vp), ("y_lo", c_vp), ("y_act", c_vp), ("y_act_lo", c_vp), ("y_bstride", c_i64), ("y_act_bstride", c_i64),
+                ("batch", c_i32), ("m_rows", c_i32), ("bk", c_i32), ("g_hint", c_i32), ("grid_hint", c_i32), ("dbl_hint", c_i32)]
+
+
 class AcLstmDesc(ctypes.Structure):
     """mirror of `struct ac_lstm_desc`"""
     _fields_ = [("pre", c_vp), ("w_hh", c_vp), ("out", c_vp), ("out_bf16", c_vp), ("skip_bf16", c_vp), ("final_bf16", c_vp),
@@ -104,6 +116,7 @@ def lib():
         L.ac_lstm_layer.argtypes = [ctypes.POINTER(AcLstmDesc), c_vp]
         L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]
+        L.ac_resunit_tc.argtypes = [ctypes.POINTER(AcResunitTcDesc), c_vp]
         L.ac_add_act_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp]
         L.ac_f32_to_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp]
         L.ac_pad_halo_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]

@@ -26,10 +26,12 @@
 
 #include "common.cuh"
 #include "sm100.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
 using namespace sm100;
+using namespace tcc;
 
 constexpr int TILE_M = 128;
 constexpr int MAX_A_STAGES = 8;
@@ -80,76 +82,6 @@ struct TcParams {
     int wide_ok;                  // every output/residual row run of 16 columns is 32-byte aligned: 256-bit stores
     long long y_bs, ya_bs, y32_bs, res_bs, out_shift, out_valid;
 };
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-__device__ __forceinline__ void add_bf16x8(float (&o)[8], const __nv_bfloat16* ptr) {
-    const uint4 r = *reinterpret_cast<const uint4*>(ptr);
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-        o[2 * i] += __low2float(h2);
-        o[2 * i + 1] += __high2float(h2);
-    }
-}
-
-// lo plane of 8 values: bf16(v - float(hi)) where hi is the already-packed bf16 rounding of v
-__device__ __forceinline__ uint4 pack_lo(const float (&v)[8], const uint4& hi) {
-    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
-    uint32_t r[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&h[i]);
-        r[i] = pack_bf16(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
-    }
-    return make_uint4(r[0], r[1], r[2], r[3]);
-}
-
-__device__ __forceinline__ void st_global_256(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
-                                              uint32_t g, uint32_t h) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
-                 "r"(g), "r"(h) : "memory");
-}
-
-__device__ __forceinline__ void add_bf16x16(float (&o)[16], const __nv_bfloat16* ptr) {
-    const uint4 r0 = reinterpret_cast<const uint4*>(ptr)[0], r1 = reinterpret_cast<const uint4*>(ptr)[1];
-    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-        o[2 * i] += __low2float(h2);
-        o[2 * i + 1] += __high2float(h2);
-    }
-}
-
-// 16 values -> one 32-byte store of the bf16 roundings (+ one of the rounding residuals when `lo` is given)
-__device__ __forceinline__ void store_bf16x16(const float (&o)[16], __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    uint32_t q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = pack_bf16(o[2 * i], o[2 * i + 1]);
-    st_global_256(hi, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
-    if (lo) {
-        uint32_t r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&q[i]);
-            r[i] = pack_bf16(o[2 * i] - __low2float(h2), o[2 * i + 1] - __high2float(h2));
-        }
-        st_global_256(lo, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
-    }
-}
-
-__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
-    return make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-}
-
-// ELU on the epilogue: exp through MUFU.EX2; abs error ~1e-7 (cancellation in exp(x)-1 near 0), far below the bf16 /
-// split-bf16 rounding that follows.
-__device__ __forceinline__ float elu_ex2(float x) { return x > 0.f ? x : exp2f(x * 1.4426950408889634f) - 1.0f; }
 
 // Epilogue warps: each item is one tcgen05.ld of 32 rows x 16 accumulator columns (lane = row).  The sixteen warps
 // (four per TMEM lane quarter) interleave over the (sub-tile, column chunk) items of the tile.
@@ -539,38 +471,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-CUtensorMapSwizzle swizzle_for(int bk) {
-    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
-int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
-}
-
-inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-
 struct MergedSrc {
     const ac_tc_src* hi;
     const ac_tc_src* lo;

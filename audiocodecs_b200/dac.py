@@ -181,14 +181,28 @@ class DAC(Codec):
         B, L, C = x.B, x.L, x.C
         dev = x.buf.device
         for i, (a1, W7, d, a2, W1) in enumerate(units):
-            hs = Act(B, L, C, dev, split=self._split(C))
-            tc.conv_tc(W7, [Src(xs, taps=7, dilation=d, shift=-3 * d)], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
             last = i == len(units) - 1
             nxt = next_alpha if last else units[i + 1][0]
             y = None if last else Act(B, L, C, dev, split=self._split_res(C))
             hl, hr = out_halo if last else (0, 0)
             ys = Act(B, L, C, dev, hl=hl, hr=hr, split=self._split(C))
-            tc.conv_tc(W1, [Src(hs)], L, res=x, y=None if last else y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
+            a = Src(xs, taps=7, dilation=d, shift=-3 * d)
+
+            def unfused(a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
+                hs = Act(B, L, C, dev, split=self._split(C))
+                tc.conv_tc(W7, [a], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
+                tc.conv_tc(W1, [Src(hs)], L, res=x, y=y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
+
+            def fused(g, dbl, a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
+                return lambda: tc.resunit_tc(W7, W1, a, L, res=x, y=y, y_act=ys, act1=ACT_SNAKE, alpha1=a2.t, act2=ACT_SNAKE,
+                                             alpha2=nxt.t, h_split=self._split(C), g_hint=g, dbl_hint=dbl, name="resunit_tc")
+
+            # one fused launch (hidden tensor on chip) when both accumulators fit tensor memory, or two tap-GEMM launches:
+            # the measured-fastest variant per layer shape
+            variants = [("unfused", unfused)]
+            if 2 * C <= 512:
+                variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)] + variants
+            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None), variants)
             x, xs = y, ys
         return xs
 

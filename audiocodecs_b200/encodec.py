@@ -150,7 +150,8 @@ class Encodec(Codec):
         k3 = self._tc_conv(sd, prefix + ".block.1")
         wsc = packing.fold_weight_norm(sd, prefix + ".shortcut.conv")[:, :, 0]
         w1 = packing.fold_weight_norm(sd, prefix + ".block.3.conv")[:, :, 0]
-        tail = TcWeights(torch.cat([wsc, w1], dim=1), sd[prefix + ".shortcut.conv.bias"] + sd[prefix + ".block.3.conv.bias"])
+        # second GEMM of the fused unit: columns = [hidden (conv_k1) | raw x (1x1 shortcut)], the two biases summed
+        tail = TcWeights(torch.cat([w1, wsc], dim=1), sd[prefix + ".shortcut.conv.bias"] + sd[prefix + ".block.3.conv.bias"])
         self._tcw.append(tail)
         return k3, tail
 
@@ -194,12 +195,25 @@ class Encodec(Codec):
         ops.add_act_bf16(h0, x, final, ACT_ELU)
 
     def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act):
-        """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe))))."""
+        """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe)))).
+        Either ONE fused launch with the hidden activation kept on chip (ac_resunit_tc; tile grouping and double
+        buffering tuned per shape) or two tap-GEMM launches -- whichever measures faster for this layer shape."""
         B, L, C = x.B, x.L, x.C
         xe.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
-        he = Act(B, L, C // 2, x.buf.device, split=C >= SPLIT_MIN_CH)
-        tc.conv_tc(Wk3, [Src(xe, taps=3, origin=-2, rows=L + 2)], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
-        tc.conv_tc(Wtail, [Src(x), Src(he)], L, y_act=ye, act=ACT_ELU, name="res_tail_tc")
+        hs = C // 2 >= SPLIT_MIN_CH
+        a = Src(xe, taps=3, origin=-2, rows=L + 2)
+
+        def unfused():
+            he = Act(B, L, C // 2, x.buf.device, split=hs)
+            tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
+            tc.conv_tc(Wtail, [Src(he), Src(x)], L, y_act=ye, act=ACT_ELU, name="res_tail_tc")
+
+        def fused(g, dbl):
+            return lambda: tc.resunit_tc(Wk3, Wtail, a, L, x=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
+                                         name="resblock_tc")
+
+        variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)] + [("unfused", unfused)]
+        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None), variants)
 
     def _encoder_tc(self, sig, vlen=None):
         B, T = sig.shape

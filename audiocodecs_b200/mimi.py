@@ -179,9 +179,22 @@ class Mimi(Codec):
         """MimiResnetBlock (HF/mimi:412-451), identity shortcut, causal zero padding (TMA out-of-bounds fill):
         x raw, xe = ELU(x) -> ye = ELU(x + conv_k1(ELU(conv_k3(xe))))."""
         B, L, C = x.B, x.L, x.C
-        he = Act(B, L, C // 2, x.buf.device, split=C // 2 >= SPLIT_MIN_CH)
-        tc.conv_tc(Wk3, [Src(xe, taps=3, shift=-2)], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
-        tc.conv_tc(Wk1, [Src(he)], L, res=x, y_act=ye, act=ACT_ELU, name="res_k1_tc")
+        hs = C // 2 >= SPLIT_MIN_CH
+        a = Src(xe, taps=3, shift=-2)
+
+        def unfused():
+            he = Act(B, L, C // 2, x.buf.device, split=hs)
+            tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
+            tc.conv_tc(Wk1, [Src(he)], L, res=x, y_act=ye, act=ACT_ELU, name="res_k1_tc")
+
+        def fused(g, dbl):
+            return lambda: tc.resunit_tc(Wk3, Wk1, a, L, res=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
+                                         name="resblock_tc")
+
+        variants = [("unfused", unfused)]
+        if C <= 256:  # fused (hidden activation on chip) when the accumulators fit tensor memory; measured-fastest variant wins
+            variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)] + variants
+        tc.autotune(("mimi_resblock", B, L, C), variants)
 
     def _tc_transformer(self, layers, tws, h):
         """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,

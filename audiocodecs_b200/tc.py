@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from ._lib import AcConvTcDesc
+from ._lib import AcConvTcDesc, AcResunitTcDesc
 
 
 class Act:
@@ -150,3 +150,93 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
         # implementation overhead and are not counted)
         by = sum(2.0 * B * s.rows * s.phases * s.act.C for s in srcs) + 2.0 * B * out_rows * out_ch
         ops._PROFILER.end("conv_tc_kernel", t0, 2.0 * B * m_rows * W.n_total * W.k_total, by, label=name)
+
+
+def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, res: Act = None, y: Act = None, y_act: Act = None,
+               act1=ops.ACT_ELU, alpha1=None, act2=ops.ACT_NONE, alpha2=None, h_split=False, bk=None, g_hint=0, grid_hint=0,
+               dbl_hint=-1, name="resunit_tc"):
+    """Fused residual unit (`ac_resunit_tc`): h = act1(conv_taps(a)); v = W2 [h | x] (+ res); y = v, y_act = act2(v).
+    `a` is a Src view of the ACTIVATED input (taps / dilation / shift / origin as for conv_tc); x: raw input of a conv
+    shortcut; res: identity skip.  Outputs are Acts with C = W2.n_total."""
+    A = a.act
+    B, cin, ch, cout = A.B, A.C, W1.n_total, W2.n_total
+    assert a.phases == 1 and W1.k_total == a.taps * cin and W2.k_total == ch + (cin if x is not None else 0)
+    d = AcResunitTcDesc()
+    d.a, d.a_lo = A.row_ptr(a.origin), A.lo_ptr(a.origin)
+    d.a_row_stride, d.a_bstride, d.a_rows = cin, A.bstride, a.rows
+    d.cin, d.taps, d.dilation, d.shift = cin, a.taps, a.dilation, a.shift
+    if x is not None:
+        assert x.C == cin and x.L == m_rows and x.B == B
+        d.x, d.x_lo, d.x_bstride = x.row_ptr(0), x.lo_ptr(0), x.bstride
+    d.w1, d.w2, d.w1_split, d.w2_split = W1.w.data_ptr(), W2.w.data_ptr(), int(W1.split), int(W2.split)
+    d.ch, d.cout, d.h_split = ch, cout, int(h_split)
+    d.bias1 = W1.bias.data_ptr() if W1.bias is not None else None
+    d.bias2 = W2.bias.data_ptr() if W2.bias is not None else None
+    d.alpha1 = alpha1.data_ptr() if alpha1 is not None else None
+    d.alpha2 = alpha2.data_ptr() if alpha2 is not None else None
+    d.act1, d.act2 = act1, act2
+    for o in (res, y, y_act):
+        assert o is None or (o.C == cout and o.L == m_rows and o.B == B)
+    if res is not None:
+        d.res, d.res_lo, d.res_bstride = res.row_ptr(0), res.lo_ptr(0), res.bstride
+    if y is not None:
+        d.y, d.y_lo, d.y_bstride = y.row_ptr(0), y.lo_ptr(0), y.bstride
+    if y_act is not None:
+        d.y_act, d.y_act_lo, d.y_act_bstride = y_act.row_ptr(0), y_act.lo_ptr(0), y_act.bstride
+    d.batch, d.m_rows, d.bk, d.g_hint, d.grid_hint, d.dbl_hint = B, m_rows, bk or pick_bk(cin), g_hint, grid_hint, dbl_hint
+    t0 = ops._PROFILER.begin() if ops._PROFILER else None
+    _lib.check(_lib.lib().ac_resunit_tc(ctypes.byref(d), ops._stream()), "ac_resunit_tc")
+    if ops._PROFILER:
+        # algorithmic bytes: the unit's logical input and output once at 2 B each (+ the skip input when it is a separate tensor)
+        by = 2.0 * B * m_rows * (cin + cout) + (2.0 * B * m_rows * cout if res is not None else 0.0)
+        ops._PROFILER.end("resunit_tc_kernel", t0, 2.0 * B * m_rows * (ch * W1.k_total + cout * W2.k_total), by, label=name)
+
+
+# ---------------------------------------------------------------------------------------------- shape-keyed autotuning
+_TUNED = {}
+TUNE = True  # False: always take the first variant
+
+
+def autotune(key, variants):
+    """variants: list of (name, fn) computing the SAME result with different tilings / kernel splits.  The first call for
+    a key times every variant on the device (best of 2 after one warm-up run, CUDA events on the current stream) and caches
+    the winner; a variant whose tiling does not fit raises and is skipped.  Later calls dispatch straight to the winner.
+    Measured choices replace hand-written heuristics: which tiling wins depends on the layer shape in ways (TMA row
+    granularity, weight re-streaming per tile, epilogue / tensor-pipe balance) that the profiles only explained afterwards."""
+    name = _TUNED.get(key)
+    if name is None:
+        if not TUNE or len(variants) == 1:
+            for vname, fn in variants:  # no tuning: the first variant whose tiling fits
+                try:
+                    out = fn()
+                except RuntimeError:
+                    continue
+                _TUNED[key] = vname
+                return out
+            raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched")
+        else:
+            saved, ops._PROFILER = ops._PROFILER, None
+            times = {}
+            for vname, fn in variants:
+                try:
+                    fn()
+                except RuntimeError:
+                    continue
+                best = float("inf")
+                for _ in range(2):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                times[vname] = best
+            ops._PROFILER = saved
+            if not times:
+                raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched")
+            name = min(times, key=times.get)
+        _TUNED[key] = name
+    for vname, fn in variants:
+        if vname == name:
+            return fn()
+    raise KeyError(name)

@@ -228,6 +228,42 @@ typedef struct ac_conv_tc_desc {
 AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
 
 /*
+ * Fused residual unit on tcgen05: two chained tap-GEMMs per tile, the hidden activation stays on chip (TMEM -> registers
+ * -> shared memory in the UMMA operand layout -> second GEMM).
+ *
+ *   h[b][m][:]  = act1(bias1 + sum_{j<taps} A[b][m + j*dilation + shift][:] . W1[:, j*cin : (j+1)*cin]^T)      (ch channels)
+ *   v[b][m][:]  = bias2 + h[b][m][:] . W2[:, 0:ch]^T  (+ X[b][m][:] . W2[:, ch:ch+cin]^T)  (+ res[b][m][:])      (cout channels)
+ *   y = bf16(v) (+ lo plane);   y_act = bf16(act2(v)) (+ lo plane)          act = AC_ACT_{NONE,ELU,SNAKE}
+ *
+ * A is the ACTIVATED input (channels-last bf16 view, rows outside [0, a_rows) read as zero; `a` points at view row 0 which may
+ * be a halo row of the buffer), X the raw input of a convolutional shortcut (EnCodec), res an identity skip (Mimi, DAC).
+ * W1 is bf16 [ch][taps*cin] and W2 bf16 [cout][ch (+cin)], each optionally the stacked pair (W_hi, W_lo) (w*_split).
+ * h_split: the hidden tile carries a lo plane (adds the h_lo * W2_hi product).  ch, cout multiples of 16, <= 256,
+ * ch + cout <= 512.  Replaces EncodecResnetBlock (HF/encodec/modeling_encodec.py:252-282), MimiResnetBlock
+ * (HF/mimi/modeling_mimi.py:412-451) and DacResidualUnit (HF/dac/modeling_dac.py:173-207) -- five to six ATen ops each.
+ */
+typedef struct ac_resunit_tc_desc {
+    const void* a;  const void* a_lo;      /* activated input: view row 0 of clip 0 (hi plane, optional lo plane) */
+    int64_t a_row_stride, a_bstride;       /* elements */
+    int32_t a_rows, cin, taps, dilation, shift;
+    const void* x;  const void* x_lo;      /* raw input [batch][m_rows][cin] of the conv shortcut, or NULL */
+    int64_t x_bstride;
+    const void* w1; const void* w2;
+    int32_t w1_split, w2_split, ch, cout, h_split;
+    const float* bias1; const float* alpha1; /* [ch] */
+    const float* bias2; const float* alpha2; /* [cout] */
+    int32_t act1, act2;
+    const void* res; const void* res_lo;   /* identity skip [batch][m_rows][cout] or NULL */
+    int64_t res_bstride;
+    void* y; void* y_lo; void* y_act; void* y_act_lo;
+    int64_t y_bstride, y_act_bstride;
+    int32_t batch, m_rows, bk, g_hint, grid_hint;
+    int32_t dbl_hint;                      /* -1 automatic; 0 / 1: single / double-buffered hidden tile and first accumulator */
+} ac_resunit_tc_desc;
+
+AC_API int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream);
+
+/*
  * Fill the halo rows of a channels-last bf16 activation buffer [batch][halo_l + rows + halo_r][ch] from its
  * valid rows: mode AC_PAD_REFLECT (EnCodec, incl. the zero-extension rule for tiny inputs via reflect_len),
  * AC_PAD_REPLICATE (Mimi downsample) or AC_PAD_ZERO.  `data` points at valid row 0 of clip 0.

@@ -34,3 +34,6 @@ for name, s, e, fl, by, label in prof.records:
     tot += ms
     print(f"{label:16s} {ms:8.3f} ms  {by / ms / 1e6:8.1f} GB/s  {fl / ms / 1e9:8.1f} TFLOP/s  ({by / 1e6:9.1f} MB, {fl / 1e9:9.1f} GFLOP)")
 print(f"total {tot:.3f} ms for {B} x {secs} s -> {B * secs / tot * 1e3:.0f} audio-s/s (sum of launches)")
+from audiocodecs_b200 import tc
+for k, v in tc._TUNED.items():
+    print("tuned", k, "->", v)

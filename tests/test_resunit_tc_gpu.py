@@ -1,0 +1,130 @@
+"""GPU: the fused residual-unit kernel (ac_resunit_tc: two chained tcgen05 GEMMs, hidden tile kept on chip) against a
+plain PyTorch fp32 reference of the same op on the same bf16-rounded operands (tolerance = bf16 rounding of the hidden
+activation and of the output; with split planes ~1e-4)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from audiocodecs_b200 import ops, tc
+from audiocodecs_b200.tc import Act, Src, TcWeights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _act_from(t, split, hl=0, hr=0):
+    """[B, L, C] fp32 -> Act holding bf16 hi (+lo) planes; returns the Act and the value it represents"""
+    B, L, C = t.shape
+    a = Act(B, L, C, DEV, hl=hl, hr=hr, zero=True, split=split)
+    hi = t.to(torch.bfloat16)
+    a.buf[:, hl:hl + L] = hi.to(DEV)
+    val = hi.float()
+    if split:
+        lo = (t - hi.float()).to(torch.bfloat16)
+        a.lo[:, hl:hl + L] = lo.to(DEV)
+        val = val + lo.float()
+    return a, val
+
+
+def _snake(x, alpha):
+    return x + torch.sin(alpha * x) ** 2 / (alpha + 1e-9)
+
+
+def _val(a):
+    v = a.data().float()
+    if a.lo is not None:
+        v = v + a.lo[:, a.hl:a.hl + a.L].float()
+    return v.cpu()
+
+
+@pytest.mark.parametrize("C,L,B,split", [(32, 1000, 3, False), (64, 777, 2, False), (128, 300, 2, True), (256, 130, 1, True)])
+def test_encodec_resblock(C, L, B, split):
+    """shortcut_1x1(x) + conv_k1(ELU(conv_k3(ELU(x)))) then the consumer's ELU; causal k3 over a 2-row halo (reflect values
+    are whatever the halo holds: here the first rows of x itself, the kernel only sees a view)."""
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, L + 2, C, generator=g)  # rows 0,1 play the halo
+    xe_full = F.elu(x)
+    w3 = torch.randn(C // 2, C, 3, generator=g) * (3 * C) ** -0.5
+    w1 = torch.randn(C, C // 2, generator=g) * (C // 2) ** -0.5
+    wsc = torch.randn(C, C, generator=g) * C ** -0.5
+    b3, b1 = torch.randn(C // 2, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    xe_act, xe_val = _act_from(xe_full[:, 2:], split, hl=2)
+    xe_act.buf[:, :2] = xe_full[:, :2].to(torch.bfloat16).to(DEV)
+    halo_val = xe_full[:, :2].to(torch.bfloat16).float()
+    if split:
+        xe_act.lo[:, :2] = (xe_full[:, :2] - halo_val).to(torch.bfloat16).to(DEV)
+        halo_val = halo_val + (xe_full[:, :2] - halo_val).to(torch.bfloat16).float()
+    x_act, x_val = _act_from(x[:, 2:], split)
+    W1 = TcWeights(w3.permute(0, 2, 1).reshape(C // 2, -1), b3)
+    W2 = TcWeights(torch.cat([w1, wsc], dim=1), b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    ye = Act(B, L, C, DEV, split=split)
+    tc.resunit_tc(W1, W2, Src(xe_act, taps=3, origin=-2, rows=L + 2), L, x=x_act, y_act=ye, act1=ops.ACT_ELU, act2=ops.ACT_ELU,
+                  h_split=split)
+    torch.cuda.synchronize()
+    a_full = torch.cat([halo_val, xe_val], dim=1).transpose(1, 2)  # [B, C, L+2]
+    h = F.elu(F.conv1d(a_full, w3, b3))
+    ref = F.elu(F.conv1d(h, w1[:, :, None], b1) + F.conv1d(x_val.transpose(1, 2), wsc[:, :, None])).transpose(1, 2)
+    got = _val(ye)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    tol = (2e-4 if split else 3e-2) * max(1.0, ref.abs().max().item())
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("C,L,B,dil,split,hsplit", [(64, 900, 2, 1, False, False), (96, 500, 2, 9, False, False), (128, 640, 1, 3, True, True),
+                                                    (192, 300, 2, 9, True, False), (256, 200, 1, 3, True, True)])
+def test_dac_residual_unit(C, L, B, dil, split, hsplit):
+    """x + conv_k1(Snake(conv_k7_dilated(Snake(x)))) with zero padding from TMA out-of-bounds fill; raw and Snake outputs."""
+    g = torch.Generator().manual_seed(C + dil)
+    x = torch.randn(B, L, C, generator=g)
+    al1, al2, al3 = (torch.rand(C, generator=g) + 0.5 for _ in range(3))
+    xs = _snake(x, al1)
+    w7 = torch.randn(C, C, 7, generator=g) * (7 * C) ** -0.5
+    w1 = torch.randn(C, C, generator=g) * C ** -0.5
+    b7, b1 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    xs_act, xs_val = _act_from(xs, split)
+    x_act, x_val = _act_from(x, True)
+    W1 = TcWeights(w7.permute(0, 2, 1).reshape(C, -1), b7)
+    W2 = TcWeights(w1, b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    y, ys = Act(B, L, C, DEV, split=True), Act(B, L, C, DEV, split=split)
+    tc.resunit_tc(W1, W2, Src(xs_act, taps=7, dilation=dil, shift=-3 * dil), L, res=x_act, y=y, y_act=ys, act1=ops.ACT_SNAKE,
+                  alpha1=al2.to(DEV), act2=ops.ACT_SNAKE, alpha2=al3.to(DEV), h_split=hsplit)
+    torch.cuda.synchronize()
+    h = _snake(F.conv1d(xs_val.transpose(1, 2), w7, b7, dilation=dil, padding=3 * dil), al2[None, :, None])
+    ref = x_val.transpose(1, 2) + F.conv1d(h, w1[:, :, None], b1)
+    ref_s = _snake(ref, al3[None, :, None]).transpose(1, 2)
+    ref = ref.transpose(1, 2)
+    got, got_s = _val(y), _val(ys)
+    assert torch.isfinite(got).all() and torch.isfinite(got_s).all()
+    tol_h = 2e-4 if hsplit else 2e-2  # bf16 rounding of the hidden activation dominates unless it carries a lo plane
+    assert (got - ref).abs().max().item() <= tol_h * max(1.0, ref.abs().max().item())
+    assert (got_s - ref_s).abs().max().item() <= (tol_h if split else 3e-2) * max(1.0, ref_s.abs().max().item())
+
+
+def test_mimi_resblock_identity_skip_many_tiles():
+    """causal zero-padded k3 (rows < 0 read as zero), identity skip, more tiles than CTAs (grid_hint) and a ragged tail"""
+    B, L, C = 5, 4000 + 37, 64
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, L, C, generator=g)
+    w3 = torch.randn(C // 2, C, 3, generator=g) * (3 * C) ** -0.5
+    w1 = torch.randn(C, C // 2, generator=g) * (C // 2) ** -0.5
+    b3, b1 = torch.randn(C // 2, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    xe_act, xe_val = _act_from(F.elu(x), False)
+    x_act, x_val = _act_from(x, False)
+    W1, W2 = TcWeights(w3.permute(0, 2, 1).reshape(C // 2, -1), b3), TcWeights(w1, b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    for g_hint, grid_hint in ((0, 0), (1, 5), (2, 3)):
+        ye = Act(B, L, C, DEV)
+        tc.resunit_tc(W1, W2, Src(xe_act, taps=3, shift=-2), L, res=x_act, y_act=ye, act1=ops.ACT_ELU, act2=ops.ACT_ELU,
+                      g_hint=g_hint, grid_hint=grid_hint)
+        torch.cuda.synchronize()
+        h = F.elu(F.conv1d(F.pad(xe_val.transpose(1, 2), (2, 0)), w3, b3))
+        ref = F.elu(x_val.transpose(1, 2) + F.conv1d(h, w1[:, :, None], b1)).transpose(1, 2)
+        got = _val(ye)
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item()), (g_hint, grid_hint)
