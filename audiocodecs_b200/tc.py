@@ -199,7 +199,7 @@ TUNE = True  # False: always take the first variant
 
 def autotune(key, variants):
     """variants: list of (name, fn) computing the SAME result with different tilings / kernel splits.  The first call for
-    a key times every variant on the device (best of 2 after one warm-up run, CUDA events on the current stream) and caches
+    a key times every variant on the device (best of 3 after one warm-up run, CUDA events on the current stream) and caches
     the winner; a variant whose tiling does not fit raises and is skipped.  Later calls dispatch straight to the winner.
     Measured choices replace hand-written heuristics: which tiling wins depends on the layer shape in ways (TMA row
     granularity, weight re-streaming per tile, epilogue / tensor-pipe balance) that the profiles only explained afterwards."""
@@ -223,7 +223,7 @@ def autotune(key, variants):
                 except RuntimeError:
                     continue
                 best = float("inf")
-                for _ in range(2):
+                for _ in range(3):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     fn()
