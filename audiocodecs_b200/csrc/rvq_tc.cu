@@ -214,8 +214,13 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
                 if (lane == 0) mbar_arrive(a_ready);
                 const float xn = half == 0 ? xn_part + peer_x[0] : peer_x[0] + xn_part;  // dims 0..63 first, on both halves
 
-                float v1 = -INFINITY, v2 = -INFINITY;
-                int i1 = 0x7fffffff, i2 = 0x7fffffff;
+                // Candidate selection: per frame the two smallest keys of this thread's 512 codes, where
+                //   key = (bits(max(dist, 0)) & ~511) | local_index,   dist = (|r|^2 + |E|^2) - 2 r.E  >= 0.
+                // Non-negative floats order like their bit patterns, so ONE integer min/max chain tracks value and index
+                // together (3 ops per code instead of compare/select pairs); dropping 9 mantissa bits (2^-14 relative)
+                // cannot push the true winner out of the top 2 unless its gap to the runner-up is below 6e-5 -- a near-tie
+                // (< 1e-4) by the parity definition -- and the two candidates are re-scored exactly below.
+                uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
                 for (int g = 0; g < groups; ++g, ++gcount) {
                     const uint32_t buf = gcount & 1;
                     mbar_wait(&tfull[buf], (gcount >> 1) & 1);
@@ -225,19 +230,32 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
                         const int col = half * 128 + cc * 16;
                         uint32_t v[16];
                         tmem_ld16(lane_addr + buf * GROUP + col, v);
+                        const float4* enp = reinterpret_cast<const float4*>(en + g * GROUP + col);
+                        float e[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t = enp[q];
+                            e[4 * q] = xn + t.x; e[4 * q + 1] = xn + t.y; e[4 * q + 2] = xn + t.z; e[4 * q + 3] = xn + t.w;
+                        }
+                        const uint32_t lbase = (uint32_t)(g * 128 + cc * 16);
                         tmem_ld_wait();
-                        const int c0 = g * GROUP + col;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float s = -((xn - 2.f * __uint_as_float(v[j])) + en[c0 + j]);  // HF/encodec:367
-                            top2_insert(s, c0 + j, v1, i1, v2, i2);
+                            const float dist = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), e[j]), 0.f);
+                            const uint32_t key = (__float_as_uint(dist) & 0xFFFFFE00u) | (lbase + j);
+                            const uint32_t t = max(k1, key);
+                            k1 = min(k1, key);
+                            k2 = min(k2, t);
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
-                // ---- merge the two halves' candidates -> the frame's top 2
+                // ---- merge the two halves' candidates -> the frame's top 2 (truncated distance, then GLOBAL index)
+                auto glob = [&](uint32_t k, int h) { const int l = (int)(k & 511u); return (l >> 7) * GROUP + h * 128 + (l & 127); };
+                float v1 = -__uint_as_float(k1 & 0xFFFFFE00u), v2 = -__uint_as_float(k2 & 0xFFFFFE00u);  // scores: larger is better
+                int i1 = glob(k1, half), i2 = glob(k2, half);
                 my_x[1] = v1; my_x[2] = __int_as_float(i1); my_x[3] = v2; my_x[4] = __int_as_float(i2);
                 epi_bar();
                 top2_insert(peer_x[1], __float_as_int(peer_x[2]), v1, i1, v2, i2);
