@@ -34,7 +34,10 @@ constexpr int MAX_A_STAGES = 8;
 constexpr int MAX_W_STAGES = 6;
 constexpr int EPI_WARPS = 16;
 constexpr int FIRST_EPI_WARP = 3;
-constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS);
+constexpr int XF_WARPS = 4;  // transform warps: raw input block -> activated operand block (raw mode)
+constexpr int FIRST_XF_WARP = FIRST_EPI_WARP + EPI_WARPS;
+constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS + XF_WARPS);
+constexpr int NBARS = 4 * MAX_A_STAGES + 2 * MAX_W_STAGES + 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_HALF = 113 * 1024;
 
@@ -51,6 +54,12 @@ struct RuParams {
     uint32_t w1_kb_bytes, w2h_kb_bytes, w2x_kb_bytes, w1_res_plane, w2h_res_plane, w2x_res_plane, w2h_res_off, w2x_res_off, w_area_bytes;
     uint32_t h_blk_bytes, h_plane_bytes;
     uint32_t tmem_cols, acc2_col, acc1_stride;
+    // raw mode: the A source is the RAW input; transform warps apply act0 (the unit's input activation) block by block into a
+    // second ring that GEMM1 reads, so the producer layer writes ONE tensor and this kernel reads it once.  x_from_a: the conv
+    // shortcut of GEMM2 reads the raw rows of the same staged blocks (no separate X loads).
+    int raw, act0, e_split, x_from_a, sc_row_off;
+    uint32_t e_stage_bytes, e_plane_bytes;
+    const float* alpha0;
     int dbl;                      // acc1 and the hidden tile are double-buffered: GEMM1 / epilogue 1 of tile i+1 overlap GEMM2 / epilogue 2 of tile i
     uint32_t h_stage_bytes;       // one hidden-tile buffer (all k-blocks, hi [+lo] planes)
     const float *bias1, *alpha1, *bias2, *alpha2;
@@ -92,8 +101,8 @@ __device__ __forceinline__ void issue_blocks(bool leader, int G, uint32_t d0, ui
 }
 
 template <int KA, int KH>
-__device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uint8_t* w_area, uint8_t* h_tile, uint64_t* a_full,
-                                         uint64_t* a_empty, uint64_t* w_full, uint64_t* w_empty, uint64_t* acc1_full,
+__device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uint8_t* e_ring, uint8_t* w_area, uint8_t* h_tile, uint64_t* a_full,
+                                         uint64_t* a_empty, uint64_t* e_full, uint64_t* e_empty, uint64_t* w_full, uint64_t* w_empty, uint64_t* acc1_full,
                                          uint64_t* h_ready, uint64_t* acc2_full, uint64_t* acc_free, uint64_t* wres_bar,
                                          uint32_t tmem_base, int total_tiles) {
     const bool leader = elect_one();
@@ -101,8 +110,9 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
     uint32_t aphase = 0, wphase = 0;
     const uint32_t idesc1 = make_idesc_bf16(TILE_M, p.ch), idesc2 = make_idesc_bf16(TILE_M, p.cout);
     constexpr uint32_t row_bytes = KA * 32;
-    const uint32_t a_ring_u = smem_u32(a_ring), w_area_u = smem_u32(w_area), h_u = smem_u32(h_tile);
+    const uint32_t a_ring_u = smem_u32(a_ring), e_ring_u = smem_u32(e_ring), w_area_u = smem_u32(w_area), h_u = smem_u32(h_tile);
     const uint32_t acc2 = tmem_base + p.acc2_col;
+    int a_base[2] = {0, 0};  // ring stage of chunk 0 of the tiles in flight (raw rows are read again by GEMM2's shortcut)
     if (p.w_resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
     // next W block: resident address or ring slot (returns hi address; lo = hi + plane).  which: 0 = W1, 1 = W2 hidden part, 2 = W2 x part
     auto w_get = [&](int which, int kb, uint32_t& w_hi, uint32_t& w_lo) {
@@ -127,18 +137,20 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
     auto gemm1 = [&](int it) {
         const uint32_t d0 = tmem_base + (p.dbl ? (it & 1) : 0) * p.acc1_stride;
         uint32_t acc = 0;
+        a_base[it & 1] = astage;
         for (int cc = 0; cc < p.chunks1; ++cc) {
-            mbar_wait(&a_full[astage], aphase);
+            mbar_wait(p.raw ? &e_full[astage] : &a_full[astage], aphase);
             tc_fence_after();
-            const uint32_t a_hi = a_ring_u + astage * p.a_stage_bytes;
+            const uint32_t a_hi = p.raw ? e_ring_u + astage * p.e_stage_bytes : a_ring_u + astage * p.a_stage_bytes;
+            const uint32_t lo_off = p.raw ? (p.e_split ? p.e_plane_bytes : 0u) : (p.a_has_lo ? p.a_plane_bytes : 0u);
             for (int j = 0; j < p.taps; ++j) {
                 uint32_t w_hi, w_lo;
                 w_get(0, j * p.chunks1 + cc, w_hi, w_lo);
-                issue_blocks<KA>(leader, p.G, d0, p.ch, a_hi + j * p.dil * row_bytes, p.a_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w1_split != 0, idesc1, acc);
+                issue_blocks<KA>(leader, p.G, d0, p.ch, a_hi + j * p.dil * row_bytes, lo_off, w_hi, w_lo, p.w1_split != 0, idesc1, acc);
                 acc = 1u;
                 w_done();
             }
-            if (leader) umma_commit(&a_empty[astage]);
+            if (leader) umma_commit(p.raw ? &e_empty[astage] : &a_empty[astage]);
             if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
         }
         if (leader) umma_commit(&acc1_full[p.dbl ? (it & 1) : 0]);
@@ -159,16 +171,32 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
             acc = 1u;
             w_done();
         }
-        for (int cc = 0; cc < p.xchunks; ++cc) {
-            mbar_wait(&a_full[astage], aphase);
-            tc_fence_after();
-            uint32_t w_hi, w_lo;
-            w_get(2, cc, w_hi, w_lo);
-            issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + astage * p.a_stage_bytes, p.x_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
-            acc = 1u;
-            w_done();
-            if (leader) umma_commit(&a_empty[astage]);
-            if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+        if (p.x_from_a) {
+            // conv shortcut from the raw rows of this tile's own staged blocks (already landed: the transform warps waited
+            // for them before signalling e_full); the blocks are released here
+            for (int cc = 0; cc < p.chunks1; ++cc) {
+                int st = a_base[it & 1] + cc;
+                if (st >= p.a_stages) st -= p.a_stages;
+                uint32_t w_hi, w_lo;
+                w_get(2, cc, w_hi, w_lo);
+                issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + st * p.a_stage_bytes + p.sc_row_off * row_bytes,
+                                 p.a_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
+                acc = 1u;
+                w_done();
+                if (leader) umma_commit(&a_empty[st]);
+            }
+        } else {
+            for (int cc = 0; cc < p.xchunks; ++cc) {
+                mbar_wait(&a_full[astage], aphase);
+                tc_fence_after();
+                uint32_t w_hi, w_lo;
+                w_get(2, cc, w_hi, w_lo);
+                issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + astage * p.a_stage_bytes, p.x_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
+                acc = 1u;
+                w_done();
+                if (leader) umma_commit(&a_empty[astage]);
+                if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+            }
         }
         if (leader) umma_commit(acc2_full);
         __syncwarp();
@@ -220,12 +248,15 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
-    uint8_t* w_area = a_ring + (size_t)p.a_stages * p.a_stage_bytes;
+    uint8_t* e_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;  // activated blocks (raw mode only)
+    uint8_t* w_area = e_ring + (p.raw ? (size_t)p.a_stages * p.e_stage_bytes : 0);
     uint8_t* h_tile = w_area + p.w_area_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(h_tile + (size_t)p.h_stage_bytes * (1 + p.dbl));
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + MAX_A_STAGES;
-    uint64_t* w_full = a_empty + MAX_A_STAGES;
+    uint64_t* e_full = a_empty + MAX_A_STAGES;
+    uint64_t* e_empty = e_full + MAX_A_STAGES;
+    uint64_t* w_full = e_empty + MAX_A_STAGES;
     uint64_t* w_empty = w_full + MAX_W_STAGES;
     uint64_t* acc1_full = w_empty + MAX_W_STAGES;  // [2]
     uint64_t* h_ready = acc1_full + 2;             // [2]
@@ -233,12 +264,14 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     uint64_t* acc_free = acc2_full + 1;
     uint64_t* wres_bar = acc_free + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
-    float* bias1_s = reinterpret_cast<float*>(bars + 36);  // 288 B into the (1024-aligned) barrier block
+    float* bias1_s = reinterpret_cast<float*>(bars + NBARS);  // 16-byte aligned: the barrier block is 1024-aligned, NBARS is even
     float* alpha1_s = bias1_s + p.ch;
     float* ralpha1_s = alpha1_s + p.ch;
     float* bias2_s = ralpha1_s + p.ch;
     float* alpha2_s = bias2_s + p.cout;
     float* ralpha2_s = alpha2_s + p.cout;
+    float* alpha0_s = ralpha2_s + p.cout;   // [cin] raw mode
+    float* ralpha0_s = alpha0_s + p.cin;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
     const int lane = threadIdx.x & 31;
@@ -250,7 +283,12 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         prefetch_tensormap(&maps.a);
         prefetch_tensormap(&maps.w1);
         prefetch_tensormap(&maps.w2h);
-        for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.a_stages; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], (p.raw && !p.x_from_a) ? XF_WARPS : 1);  // released by the transform warps, or by an MMA commit
+            mbar_init(&e_full[i], XF_WARPS);
+            mbar_init(&e_empty[i], 1);
+        }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&h_ready[i], EPI_WARPS); }
         mbar_init(acc2_full, 1);
@@ -271,6 +309,12 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         alpha2_s[i] = a;
         ralpha2_s[i] = 1.0f / (a + 1e-9f);
     }
+    if (p.raw)
+        for (int i = threadIdx.x; i < p.cin; i += THREADS) {
+            const float a = p.act0 == AC_ACT_SNAKE ? p.alpha0[i] : 1.f;
+            alpha0_s[i] = a;
+            ralpha0_s[i] = 1.0f / (a + 1e-9f);
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,7 +341,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             auto load2 = [&](int it) {  // raw-x blocks of GEMM2
                 const int tile = blockIdx.x + it * gridDim.x;
                 const int mg = tile % p.m_groups, b = tile / p.m_groups, m0 = mg * p.G * TILE_M;
-                for (int cc = 0; cc < p.xchunks; ++cc) {
+                for (int cc = 0; cc < (p.x_from_a ? 0 : p.xchunks); ++cc) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&a_full[stage], p.x_pieces * x_piece * (1 + p.x_has_lo));
                     uint8_t* dst = a_ring + (size_t)stage * p.a_stage_bytes;
@@ -368,7 +412,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-#define AC_RU_ARGS p, a_ring, w_area, h_tile, a_full, a_empty, w_full, w_empty, acc1_full, h_ready, acc2_full, acc_free, wres_bar, tmem_base, total_tiles
+#define AC_RU_ARGS p, a_ring, e_ring, w_area, h_tile, a_full, a_empty, e_full, e_empty, w_full, w_empty, acc1_full, h_ready, acc2_full, acc_free, wres_bar, tmem_base, total_tiles
         const int ka = p.bk / 16, kh = p.bkh / 16;
         if (ka == 4 && kh == 4) mma_role<4, 4>(AC_RU_ARGS);
         else if (ka == 4 && kh == 2) mma_role<4, 2>(AC_RU_ARGS);
@@ -380,6 +424,67 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         else if (ka == 1 && kh == 2) mma_role<1, 2>(AC_RU_ARGS);
         else mma_role<1, 1>(AC_RU_ARGS);
 #undef AC_RU_ARGS
+    } else if (warp >= FIRST_XF_WARP) {
+        // ================================================================= transform warps (raw mode): block by block,
+        // activated = act0(raw_hi [+ raw_lo]) written at the same (swizzled) offsets of the E ring; elementwise, so the
+        // operand layout TMA produced is preserved.  Zero-filled (out-of-bounds) rows stay zero: ELU(0) = Snake(0) = 0.
+        if (p.raw) {
+            const int t = threadIdx.x - 32 * FIRST_XF_WARP;
+            const int upr = p.bk / 8;                                   // 16-byte units per block row
+            const int xshift = p.bk == 64 ? 0 : (p.bk == 32 ? 1 : 2);
+            const int units = p.a_pieces * p.a_box_rows * upr;
+            int stage = 0;
+            uint32_t phase = 0;
+            const int blocks = my_tiles * p.chunks1;
+            for (int n = 0, cc = 0; n < blocks; ++n) {
+                mbar_wait(&a_full[stage], phase);
+                mbar_wait(&e_empty[stage], phase ^ 1);
+                const uint8_t* src = a_ring + (size_t)stage * p.a_stage_bytes;
+                uint8_t* dst = e_ring + (size_t)stage * p.e_stage_bytes;
+                for (int u = t; u < units; u += 32 * XF_WARPS) {
+                    const uint4 h = *reinterpret_cast<const uint4*>(src + (size_t)u * 16);
+                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(hp[i]); v[2 * i + 1] = __high2float(hp[i]); }
+                    if (p.a_has_lo) {
+                        const uint4 l = *reinterpret_cast<const uint4*>(src + p.a_plane_bytes + (size_t)u * 16);
+                        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { v[2 * i] += __low2float(lp[i]); v[2 * i + 1] += __high2float(lp[i]); }
+                    }
+                    if (p.act0 == AC_ACT_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = elu_ex2(v[i]);
+                    } else {
+                        const int row = u / upr, pu = u - row * upr;
+                        const int ch = cc * p.bk + ((pu ^ ((row >> xshift) & (upr - 1))) << 3);  // logical channel of this unit
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float4 a = *reinterpret_cast<const float4*>(alpha0_s + ch + 4 * q);
+                            const float4 r = *reinterpret_cast<const float4*>(ralpha0_s + ch + 4 * q);
+                            const float al[4] = {a.x, a.y, a.z, a.w}, ra[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float sn = __sinf(al[i] * v[4 * q + i]);
+                                v[4 * q + i] = fmaf(ra[i], sn * sn, v[4 * q + i]);
+                            }
+                        }
+                    }
+                    const uint4 q = pack8(v);
+                    *reinterpret_cast<uint4*>(dst + (size_t)u * 16) = q;
+                    if (p.e_split) *reinterpret_cast<uint4*>(dst + p.e_plane_bytes + (size_t)u * 16) = pack_lo(v, q);
+                }
+                fence_proxy_async();  // generic-proxy stores of the activated block -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&e_full[stage]);
+                    if (!p.x_from_a) mbar_arrive(&a_empty[stage]);
+                }
+                if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+                if (++cc == p.chunks1) cc = 0;
+            }
+        }
     } else {
         // ================================================================= epilogue warps
         const int quarter = warp & 3;
@@ -533,11 +638,15 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     AC_REQUIRE(encode, "ac_resunit_tc: cuTensorMapEncodeTiled not available");
 
     const int w1_split = d->w1_split ? 1 : 0, w2_split = d->w2_split ? 1 : 0, h_split = d->h_split ? 1 : 0;
-    const int a_has_lo = d->a_lo ? 1 : 0, x_has_lo = (d->x && d->x_lo) ? 1 : 0, has_x = d->x ? 1 : 0;
+    const int a_has_lo = d->a_lo ? 1 : 0, x_has_lo = (d->x && d->x_lo) ? 1 : 0, has_x = (d->x || d->x_from_a) ? 1 : 0;
     const int any_lo = a_has_lo | x_has_lo;
     const int sms = sm_count();
     const long long m_tiles = (d->m_rows + TILE_M - 1) / TILE_M;
-    const size_t fixed = 1024 /*align slack*/ + 36 * 8 + (size_t)(d->ch + d->cout) * 12 + 64;
+    const int raw = d->act0 != AC_ACT_NONE ? 1 : 0, e_split = (raw && d->e_split) ? 1 : 0, x_from_a = d->x_from_a ? 1 : 0;
+    AC_REQUIRE(!x_from_a || (raw && !d->x && d->x_row_off >= 0 && d->x_row_off <= (d->taps - 1) * d->dilation),
+               "ac_resunit_tc: x_from_a needs raw mode, no separate x and the raw rows inside the staged block");
+    AC_REQUIRE(!raw || d->act0 != AC_ACT_SNAKE || d->alpha0, "ac_resunit_tc: snake input activation needs alpha0");
+    const size_t fixed = 1024 /*align slack*/ + NBARS * 8 + (size_t)(d->ch + d->cout) * 12 + (size_t)d->cin * 8 + 64;
     const int halo = (d->taps - 1) * d->dilation;
 
     RuParams p{};
@@ -565,7 +674,10 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 const int x_pieces = (G * TILE_M + 255) / 256, x_box = G * TILE_M / x_pieces;
                 uint32_t a_plane = round_up((uint32_t)a_pieces * a_box * bk * 2, 1024);
                 if (has_x) { const uint32_t xb = (uint32_t)G * TILE_M * bk * 2; if (xb > a_plane) a_plane = xb; }
-                const uint32_t a_stage = a_plane * (1 + any_lo);
+                const uint32_t a_stage_raw = a_plane * (1 + any_lo);
+                const uint32_t e_stage = raw ? a_plane * (1 + e_split) : 0;
+                const uint32_t a_stage = a_stage_raw + e_stage;  // ring cost per stage (raw block + activated block)
+                const int min_a = x_from_a ? (1 + dbl) * chunks1 : 2;
                 const uint32_t h_blk = (uint32_t)G * TILE_M * bkh * 2, h_plane = h_blk * hblocks;
                 const size_t h_stage = (size_t)h_plane * (1 + h_split);
                 const size_t h_total = h_stage * (1 + dbl);
@@ -598,11 +710,11 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                     w_area = (size_t)w_stages * w_stage;
                 }
                 if (a_stages > MAX_A_STAGES) a_stages = MAX_A_STAGES;
-                if (a_stages < 2 || (pass == 0 && a_stages < 3)) continue;
+                if (a_stages < 2 || a_stages < min_a || (pass == 0 && a_stages < (x_from_a ? min_a + 1 : 3))) continue;
                 p.bk = bk; p.bkh = bkh; p.G = G; p.chunks1 = chunks1; p.hblocks = hblocks; p.xchunks = xchunks;
                 p.a_pieces = a_pieces; p.a_box_rows = a_box; p.x_pieces = x_pieces; p.x_box_rows = x_box;
                 p.a_stages = a_stages; p.w_stages = w_stages; p.w_resident = resident ? 1 : 0;
-                p.a_stage_bytes = a_stage; p.a_plane_bytes = a_plane; p.w_stage_bytes = w_stage; p.w_plane_bytes = w_plane;
+                p.a_stage_bytes = a_stage_raw; p.a_plane_bytes = a_plane; p.e_stage_bytes = e_stage; p.e_plane_bytes = a_plane; p.w_stage_bytes = w_stage; p.w_plane_bytes = w_plane;
                 p.w1_kb_bytes = w1_kb; p.w2h_kb_bytes = w2h_kb; p.w2x_kb_bytes = w2x_kb;
                 p.w1_res_plane = (uint32_t)nkb1 * w1_kb; p.w2h_res_plane = (uint32_t)hblocks * w2h_kb; p.w2x_res_plane = (uint32_t)xchunks * w2x_kb;
                 p.w2h_res_off = (uint32_t)nkb1 * w1_kb * (1 + w1_split);
@@ -626,7 +738,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
         AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (A lo) failed: %d", r);
     }
     maps.x = maps.a; maps.x_lo = maps.a;
-    if (has_x) {
+    if (has_x && !x_from_a) {
         r = encode_act_map(encode, &maps.x, d->x, d->cin, d->m_rows, d->cin, d->x_bstride, d->batch, p.bk, p.x_box_rows);
         AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (X) failed: %d", r);
         if (x_has_lo) {
@@ -641,6 +753,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     r = encode_w_map(encode, &maps.w2x, d->w2, d->ch + (has_x ? d->cin : 0), d->cout, 1 + w2_split, p.bk);
     AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (W2 x part) failed: %d", r);
 
+    p.raw = raw; p.act0 = d->act0; p.e_split = e_split; p.x_from_a = x_from_a; p.sc_row_off = d->x_row_off; p.alpha0 = d->alpha0;
     p.cin = d->cin; p.taps = d->taps; p.dil = d->dilation; p.shift = d->shift; p.a_has_lo = a_has_lo; p.x_has_lo = x_has_lo;
     p.ch = d->ch; p.cout = d->cout; p.h_split = h_split; p.w1_split = w1_split; p.w2_split = w2_split;
     p.m_rows = d->m_rows; p.m_groups = (d->m_rows + p.G * TILE_M - 1) / (p.G * TILE_M); p.batch = d->batch;
@@ -650,7 +763,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     p.res_bs = d->res_bstride; p.y_bs = d->y_bstride; p.ya_bs = d->y_act_bstride;
 
     // every CTA owns its SM (tensor memory is allocated in full): ask for more than half the shared memory
-    size_t smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + p.w_area_bytes + (size_t)p.h_stage_bytes * (1 + p.dbl);
+    size_t smem = fixed + (size_t)p.a_stages * (p.a_stage_bytes + p.e_stage_bytes) + p.w_area_bytes + (size_t)p.h_stage_bytes * (1 + p.dbl);
     AC_REQUIRE(smem <= (size_t)SMEM_LIMIT, "ac_resunit_tc: shared memory %zu", smem);
     if (smem <= (size_t)SMEM_HALF + 1024) smem = SMEM_HALF + 2048;
     static bool attr_set = false;

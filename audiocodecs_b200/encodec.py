@@ -14,6 +14,10 @@ __all__ = ["Encodec"]
 
 RATIOS = (8, 5, 4, 2)  # facebook/encodec_24khz upsampling_ratios (HF/encodec/configuration_encodec.py)
 SPLIT_MIN_CH = 128     # activations with >= this many channels travel as (hi, lo) bf16 pairs (precision)
+RAW_MAX_CH = 0         # residual blocks with <= this many channels take RAW x and apply their input ELU on chip (raw mode of
+                       # ac_resunit_tc: the producer layer writes one tensor instead of a raw and an activated copy).  Measured at
+                       # 64: producers 25-35 % faster, but the blocks themselves 1.8x slower (raw + activated blocks halve the ring
+                       # depth that fits shared memory) -- a net loss of 0.8 ms per step, so it is off
 _VALID_BW = (1.5, 3.0, 6.0, 12.0, 24.0)
 
 
@@ -197,10 +201,22 @@ class Encodec(Codec):
     def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act):
         """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe)))).
         Either ONE fused launch with the hidden activation kept on chip (ac_resunit_tc; tile grouping and double
-        buffering tuned per shape) or two tap-GEMM launches -- whichever measures faster for this layer shape."""
+        buffering tuned per shape) or two tap-GEMM launches -- whichever measures faster for this layer shape.
+        xe is None in raw mode (C <= RAW_MAX_CH): x itself carries the 2-row halo, the kernel applies the input ELU on
+        chip and reads the raw rows of the same staged blocks for the shortcut."""
         B, L, C = x.B, x.L, x.C
-        xe.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
         hs = C // 2 >= SPLIT_MIN_CH
+        if xe is None:
+            x.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
+            a = Src(x, taps=3, origin=-2, rows=L + 2)
+
+            def raw(g, dbl):
+                return lambda: tc.resunit_tc(Wk3, Wtail, a, L, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, act0=ACT_ELU,
+                                             e_split=x.lo is not None, x_from_a=True, g_hint=g, dbl_hint=dbl, name="resblock_tc")
+
+            tc.autotune(("encodec_resblock_raw", B, L, C), [(f"raw_g{g}_d{dbl}", raw(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)])
+            return
+        xe.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
         a = Src(xe, taps=3, origin=-2, rows=L + 2)
 
         def unfused():
@@ -218,8 +234,9 @@ class Encodec(Codec):
     def _encoder_tc(self, sig, vlen=None):
         B, T = sig.shape
         dev = sig.device
-        x = Act(B, T, 32, dev)
-        xe = Act(B, T, 32, dev, hl=2)
+        raw = 32 <= RAW_MAX_CH
+        x = Act(B, T, 32, dev, hl=2 if raw else 0)
+        xe = None if raw else Act(B, T, 32, dev, hl=2)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU, vlen=vlen)
         L = T
         for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):
@@ -230,8 +247,9 @@ class Encodec(Codec):
             self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
             ye.fill_halo(PAD_REFLECT, max(r, extra) + 1 if L <= max(r, extra) else 0)
             last = i == len(self._tenc) - 1
-            x = Act(B, Lout, 2 * C, dev, split=2 * C >= SPLIT_MIN_CH)
-            xe = None if last else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= SPLIT_MIN_CH)
+            raw = not last and 2 * C <= RAW_MAX_CH
+            x = Act(B, Lout, 2 * C, dev, hl=2 if raw else 0, split=2 * C >= SPLIT_MIN_CH)
+            xe = None if (last or raw) else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= SPLIT_MIN_CH)
             tc.conv_tc(Wdown, [Src(ye, taps=2, origin=-r, phases=r, rows=Lout + 1)], Lout, y=x, y_act=xe, act=ACT_ELU,
                        name="down_tc")
             L = Lout
@@ -257,8 +275,9 @@ class Encodec(Codec):
             C = ye.C // 2
             Lout = L * r
             sp = C >= SPLIT_MIN_CH
-            x = Act(B, Lout, C, dev, split=sp)
-            xe = Act(B, Lout, C, dev, hl=2, split=sp)
+            raw = C <= RAW_MAX_CH
+            x = Act(B, Lout, C, dev, hl=2 if raw else 0, split=sp)
+            xe = None if raw else Act(B, Lout, C, dev, hl=2, split=sp)
             # transposed conv: 2-tap GEMM over n = (phase, cout); row -1 reads as zero (TMA OOB fill)
             tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C,
                        name="convtr_tc")

@@ -154,13 +154,14 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
 
 def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, res: Act = None, y: Act = None, y_act: Act = None,
                act1=ops.ACT_ELU, alpha1=None, act2=ops.ACT_NONE, alpha2=None, h_split=False, bk=None, g_hint=0, grid_hint=0,
-               dbl_hint=-1, name="resunit_tc"):
+               dbl_hint=-1, act0=ops.ACT_NONE, alpha0=None, e_split=False, x_from_a=False, name="resunit_tc"):
     """Fused residual unit (`ac_resunit_tc`): h = act1(conv_taps(a)); v = W2 [h | x] (+ res); y = v, y_act = act2(v).
     `a` is a Src view of the ACTIVATED input (taps / dilation / shift / origin as for conv_tc); x: raw input of a conv
-    shortcut; res: identity skip.  Outputs are Acts with C = W2.n_total."""
+    shortcut; res: identity skip.  With act0 the view is of the RAW input and the kernel applies the unit's input activation on
+    chip (x_from_a: the conv shortcut reads the same staged raw blocks).  Outputs are Acts with C = W2.n_total."""
     A = a.act
     B, cin, ch, cout = A.B, A.C, W1.n_total, W2.n_total
-    assert a.phases == 1 and W1.k_total == a.taps * cin and W2.k_total == ch + (cin if x is not None else 0)
+    assert a.phases == 1 and W1.k_total == a.taps * cin and W2.k_total == ch + (cin if (x is not None or x_from_a) else 0)
     d = AcResunitTcDesc()
     d.a, d.a_lo = A.row_ptr(a.origin), A.lo_ptr(a.origin)
     d.a_row_stride, d.a_bstride, d.a_rows = cin, A.bstride, a.rows
@@ -175,6 +176,9 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
     d.alpha1 = alpha1.data_ptr() if alpha1 is not None else None
     d.alpha2 = alpha2.data_ptr() if alpha2 is not None else None
     d.act1, d.act2 = act1, act2
+    d.act0, d.e_split, d.x_from_a = act0, int(e_split), int(x_from_a)
+    d.x_row_off = -(a.shift + a.origin)  # view row 0 is buffer row `origin`: raw x[m] sits x_row_off rows into the tile's block
+    d.alpha0 = alpha0.data_ptr() if alpha0 is not None else None
     for o in (res, y, y_act):
         assert o is None or (o.C == cout and o.L == m_rows and o.B == B)
     if res is not None:

@@ -235,7 +235,7 @@ AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
  *   v[b][m][:]  = bias2 + h[b][m][:] . W2[:, 0:ch]^T  (+ X[b][m][:] . W2[:, ch:ch+cin]^T)  (+ res[b][m][:])      (cout channels)
  *   y = bf16(v) (+ lo plane);   y_act = bf16(act2(v)) (+ lo plane)          act = AC_ACT_{NONE,ELU,SNAKE}
  *
- * A is the ACTIVATED input (channels-last bf16 view, rows outside [0, a_rows) read as zero; `a` points at view row 0 which may
+ * A is the ACTIVATED input -- or, in raw mode (act0), the raw input activated on chip -- (channels-last bf16 view, rows outside [0, a_rows) read as zero; `a` points at view row 0 which may
  * be a halo row of the buffer), X the raw input of a convolutional shortcut (EnCodec), res an identity skip (Mimi, DAC).
  * W1 is bf16 [ch][taps*cin] and W2 bf16 [cout][ch (+cin)], each optionally the stacked pair (W_hi, W_lo) (w*_split).
  * h_split: the hidden tile carries a lo plane (adds the h_lo * W2_hi product).  ch, cout multiples of 16, <= 256,
@@ -259,6 +259,13 @@ typedef struct ac_resunit_tc_desc {
     int64_t y_bstride, y_act_bstride;
     int32_t batch, m_rows, bk, g_hint, grid_hint;
     int32_t dbl_hint;                      /* -1 automatic; 0 / 1: single / double-buffered hidden tile and first accumulator */
+    /* raw mode (act0 != AC_ACT_NONE): `a` is the RAW input and the kernel applies the unit's input activation act0 (ELU, or
+       Snake with alpha0[cin]) on chip, block by block, before GEMM1 -- the producer layer then writes one tensor instead of a
+       raw and an activated copy.  e_split: the activated operand carries a lo plane.  x_from_a: the conv shortcut reads the raw
+       rows of the same staged blocks (x must be NULL; see x_row_off). */
+    int32_t act0, e_split, x_from_a;
+    const float* alpha0;
+    int32_t x_row_off;                     /* x_from_a: view row (m + shift + x_row_off) holds raw x[m]; 0 <= x_row_off <= (taps-1)*dilation */
 } ac_resunit_tc_desc;
 
 AC_API int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream);

@@ -128,3 +128,72 @@ def test_mimi_resblock_identity_skip_many_tiles():
         got = _val(ye)
         assert torch.isfinite(got).all()
         assert (got - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item()), (g_hint, grid_hint)
+
+
+@pytest.mark.parametrize("C,L,B,split,g,dbl", [(32, 1500, 3, False, 0, -1), (64, 777, 2, False, 2, 1), (64, 2000, 2, False, 4, 0),
+                                               (64, 5000, 1, False, 1, 1), (32, 40, 2, False, 1, 0)])
+def test_encodec_resblock_raw_mode(C, L, B, split, g, dbl):
+    """raw mode: the kernel gets RAW x (2-row halo), applies ELU on chip for GEMM1 and reads the raw rows of the same
+    staged blocks for the 1x1 shortcut (x_from_a): one input tensor, read once."""
+    gen = torch.Generator().manual_seed(100 + C)
+    x = torch.randn(B, L + 2, C, generator=gen)
+    w3 = torch.randn(C // 2, C, 3, generator=gen) * (3 * C) ** -0.5
+    w1 = torch.randn(C, C // 2, generator=gen) * (C // 2) ** -0.5
+    wsc = torch.randn(C, C, generator=gen) * C ** -0.5
+    b3, b1 = torch.randn(C // 2, generator=gen) * 0.1, torch.randn(C, generator=gen) * 0.1
+    x_act, x_val = _act_from(x[:, 2:], split, hl=2)
+    halo = x[:, :2].to(torch.bfloat16)
+    x_act.buf[:, :2] = halo.to(DEV)
+    halo_val = halo.float()
+    if split:
+        hlo = (x[:, :2] - halo.float()).to(torch.bfloat16)
+        x_act.lo[:, :2] = hlo.to(DEV)
+        halo_val = halo_val + hlo.float()
+    W1 = TcWeights(w3.permute(0, 2, 1).reshape(C // 2, -1), b3)
+    W2 = TcWeights(torch.cat([w1, wsc], dim=1), b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    ye = Act(B, L, C, DEV, split=split)
+    tc.resunit_tc(W1, W2, Src(x_act, taps=3, origin=-2, rows=L + 2), L, y_act=ye, act1=ops.ACT_ELU, act2=ops.ACT_ELU, h_split=split,
+                  act0=ops.ACT_ELU, e_split=split, x_from_a=True, g_hint=g, dbl_hint=dbl)
+    torch.cuda.synchronize()
+    full = torch.cat([halo_val, x_val], dim=1)
+    xe = F.elu(full)
+    if not split:
+        xe = xe.to(torch.bfloat16).float()  # the activated operand is a single bf16 plane
+    h = F.elu(F.conv1d(xe.transpose(1, 2), w3, b3))
+    ref = F.elu(F.conv1d(h, w1[:, :, None], b1) + F.conv1d(x_val.transpose(1, 2), wsc[:, :, None])).transpose(1, 2)
+    got = _val(ye)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    tol = (2e-4 if split else 3e-2) * max(1.0, ref.abs().max().item())
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("C,L,B,dil", [(64, 900, 2, 1), (96, 500, 2, 9), (128, 640, 1, 3), (192, 300, 2, 9)])
+def test_dac_residual_unit_raw_mode(C, L, B, dil):
+    """raw mode with Snake: x (hi + lo planes) is the only input -- activated on chip for the dilated k7 conv, added back
+    as the identity skip in epilogue 2."""
+    gen = torch.Generator().manual_seed(200 + C + dil)
+    x = torch.randn(B, L, C, generator=gen)
+    al1, al2, al3 = (torch.rand(C, generator=gen) + 0.5 for _ in range(3))
+    w7 = torch.randn(C, C, 7, generator=gen) * (7 * C) ** -0.5
+    w1 = torch.randn(C, C, generator=gen) * C ** -0.5
+    b7, b1 = torch.randn(C, generator=gen) * 0.1, torch.randn(C, generator=gen) * 0.1
+    x_act, x_val = _act_from(x, True)
+    W1, W2 = TcWeights(w7.permute(0, 2, 1).reshape(C, -1), b7), TcWeights(w1, b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    y, ys = Act(B, L, C, DEV, split=True), Act(B, L, C, DEV, split=False)
+    tc.resunit_tc(W1, W2, Src(x_act, taps=7, dilation=dil, shift=-3 * dil), L, res=x_act, y=y, y_act=ys, act1=ops.ACT_SNAKE,
+                  alpha1=al2.to(DEV), act2=ops.ACT_SNAKE, alpha2=al3.to(DEV), act0=ops.ACT_SNAKE, alpha0=al1.to(DEV))
+    torch.cuda.synchronize()
+    xs = _snake(x_val, al1).to(torch.bfloat16).float()
+    h = _snake(F.conv1d(xs.transpose(1, 2), w7, b7, dilation=dil, padding=3 * dil), al2[None, :, None])
+    ref = x_val.transpose(1, 2) + F.conv1d(h, w1[:, :, None], b1)
+    ref_s = _snake(ref, al3[None, :, None]).transpose(1, 2)
+    ref = ref.transpose(1, 2)
+    got, got_s = _val(y), _val(ys)
+    assert torch.isfinite(got).all() and torch.isfinite(got_s).all()
+    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert (got_s - ref_s).abs().max().item() <= 3e-2 * max(1.0, ref_s.abs().max().item())
