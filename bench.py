@@ -31,9 +31,9 @@ WORKLOADS = {
 }
 
 
-# per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed ncu
-# captures (profiles/README.md); bytes per launch averaged over the captured launches, None when not captured
-NCU_TRAFFIC = {"conv_tc_kernel": None, "lstm_tc_kernel": 478.4e6}
+# per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, averaged over every launch of the kernel in one
+# full-size EnCodec step) from the committed ncu launch list profiles/r01c_launches.csv; None when not captured
+NCU_TRAFFIC = {"conv_tc_kernel": 1.097e9, "resunit_tc_kernel": 1.938e9, "lstm_tc_kernel": 4.759e8, "rvq_encode_tc_kernel": 3.28e7}
 
 
 def load_peaks():
@@ -226,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         roofline = {"kernel": name, "bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                     "frac": round(tflops / peaks["tf_sus"], 4)}
-    ncu = NCU_TRAFFIC.get(name)
+    ncu = NCU_TRAFFIC.get(name) if args.codec in ("encodec", "encodec32") else None
     roofline.update({"traffic": ncu, "peak_source": peaks["src"] + (" (copy bandwidth)" if roofline["bound"] == "hbm" else " (sustained bf16)"),
                      "flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
                      "tensor_tflops": round(tflops, 2), "launches_per_step": d["n"], "ms_per_step": round(d["ms"], 3),
