@@ -61,14 +61,6 @@ class AcResunitTcDesc(ctypes.Structure):
                 ("act0", c_i32), ("e_split", c_i32), ("x_from_a", c_i32), ("alpha0", c_vp), ("x_row_off", c_i32)]
 
 
-class AcLstmDesc(ctypes.Structure):
-    """mirror of `struct ac_lstm_desc`"""
-    _fields_ = [("pre", c_vp), ("w_hh", c_vp), ("out", c_vp), ("out_bf16", c_vp), ("skip_bf16", c_vp), ("final_bf16", c_vp),
-                ("skip_bstride", c_i64), ("final_bstride", c_i64), ("final_act", c_i32),
-                ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("sync_ws", c_vp),
-                ("out_lo", c_vp), ("skip_lo", c_vp), ("final_lo", c_vp)]
-
-
 class AcLstmTcDesc(ctypes.Structure):
     """mirror of `struct ac_lstm_tc_desc`"""
     _fields_ = [("pre", c_vp), ("w_hh_bf16", c_vp), ("out_hi", c_vp), ("out_lo", c_vp), ("skip_hi", c_vp), ("skip_lo", c_vp),
@@ -114,7 +106,6 @@ def lib():
                                          c_i32, c_i32, c_i32, c_vp]
         L.ac_conv_last_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_lstm_tc.argtypes = [ctypes.POINTER(AcLstmTcDesc), c_vp]
-        L.ac_lstm_layer.argtypes = [ctypes.POINTER(AcLstmDesc), c_vp]
         L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]
         L.ac_resunit_tc.argtypes = [ctypes.POINTER(AcResunitTcDesc), c_vp]

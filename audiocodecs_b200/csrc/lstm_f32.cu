@@ -194,9 +194,3 @@ extern "C" int ac_lstm_layer_f32(const float* pre, const float* w_hh, const floa
                                  int32_t batch, int32_t steps, int32_t hidden, int32_t* sync_ws, void* stream) {
     return lstm_launch(pre, w_hh, skip, out, batch, steps, hidden, sync_ws, nullptr, nullptr, nullptr, 0, 0, 0, stream);
 }
-
-extern "C" int ac_lstm_layer(const ac_lstm_desc* d, void* stream) {
-    AC_REQUIRE(d, "ac_lstm_layer: null descriptor");
-    return lstm_launch(d->pre, d->w_hh, nullptr, d->out, d->batch, d->steps, d->hidden, d->sync_ws, d->out_bf16, d->skip_bf16,
-                       d->final_bf16, d->skip_bstride, d->final_bstride, d->final_act, stream, d->out_lo, d->skip_lo, d->final_lo);
-}

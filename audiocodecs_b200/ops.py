@@ -176,31 +176,6 @@ def lstm_layer(pre, w_hh, skip, sync_ws):
     return out
 
 
-def lstm_layer_bf16(pre, w_hh, sync_ws, out_bf16=None, skip=None, final=None, final_act=ACT_NONE):
-    """bf16-pipeline LSTM layer: pre [B,T,4C] fp32 -> h; optional bf16 copy of h, and final = act(h + skip)
-    written into a tc.Act (skip: tc.Act)."""
-    from ._lib import AcLstmDesc
-    _need_cuda(pre, w_hh)
-    B, T, C4 = pre.shape
-    C = C4 // 4
-    out = torch.empty((B, T, C), device=pre.device, dtype=torch.float32)
-    d = AcLstmDesc()
-    d.pre, d.w_hh, d.out = pre.data_ptr(), w_hh.data_ptr(), out.data_ptr()
-    if out_bf16 is not None:  # tc.Act without halo
-        d.out_bf16 = out_bf16.row_ptr(0)
-        d.out_lo = out_bf16.lo_ptr(0)
-    if skip is not None:
-        d.skip_bf16, d.skip_bstride, d.skip_lo = skip.row_ptr(0), skip.bstride, skip.lo_ptr(0)
-    if final is not None:
-        d.final_bf16, d.final_bstride, d.final_lo = final.row_ptr(0), final.bstride, final.lo_ptr(0)
-    d.final_act, d.batch, d.steps, d.hidden, d.sync_ws = final_act, B, T, C, sync_ws.data_ptr()
-    t0 = _PROFILER.begin() if _PROFILER else None
-    _lib.check(_lib.lib().ac_lstm_layer(ctypes.byref(d), _stream()), "ac_lstm_layer")
-    if _PROFILER:
-        _PROFILER.end("lstm_layer_f32", t0, 2.0 * B * T * 4 * C * C, 4.0 * (pre.numel() + out.numel()))
-    return out
-
-
 def conv_first_bf16(spec, sig, y=None, y_act=None, act=ACT_NONE, vlen=None, pad_left=None, alpha=None):
     """Cin=1 first layer of the bf16 pipeline: sig [B,T] fp32 -> tc.Act outputs (raw / activated)."""
     _need_cuda(sig, spec.w)

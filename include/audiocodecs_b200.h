@@ -90,21 +90,6 @@ AC_API int ac_conv1d_f32(const ac_conv_f32* p, void* stream);
 AC_API int ac_lstm_layer_f32(const float* pre, const float* w_hh, const float* skip, float* out,
                       int32_t batch, int32_t steps, int32_t hidden, int32_t* sync_ws, void* stream);
 
-/* Same layer with the bf16 pipeline's edges: optional bf16 copy of h (input of the next layer's W_ih GEMM),
- * bf16 skip input, and a bf16 output final[b][t][C] = act(h + skip) (clip stride final_bstride elements)
- * which is what the consumer conv reads.  `out` (fp32 [B][T][C]) is always written: it carries h[t-1]. */
-typedef struct ac_lstm_desc {
-    const float* pre; const float* w_hh; float* out;
-    void* out_bf16;            /* bf16 [B][T][C] or NULL */
-    const void* skip_bf16;     /* bf16 [B][T][C] (clip stride skip_bstride) or NULL */
-    void* final_bf16;          /* bf16 act(h + skip) or NULL */
-    int64_t skip_bstride, final_bstride;
-    int32_t final_act;         /* AC_ACT_NONE / AC_ACT_ELU */
-    int32_t batch, steps, hidden;
-    int32_t* sync_ws;
-    void* out_lo; const void* skip_lo; void* final_lo; /* optional lo planes (x - bf16(x)) of out_bf16 / skip_bf16 / final_bf16 */
-} ac_lstm_desc;
-AC_API int ac_lstm_layer(const ac_lstm_desc* d, void* stream);
 
 /*
  * Tensor-core LSTM layer recurrence (hidden = 512): one cluster of 16 CTAs per 16 clips, W_hh (bf16) resident in
