@@ -93,7 +93,7 @@ def lib():
         L.ac_abi_version.restype = c_i32
         L.ac_conv1d_f32.argtypes = [ctypes.POINTER(AcConvF32), c_vp]
         L.ac_lstm_layer_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]
-        L.ac_rvq_encode_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_rvq_encode_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_rvq_encode_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_rvq_decode_f32.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_resample_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]

@@ -125,6 +125,9 @@ class Mimi(Codec):
         cb = torch.stack(cbs).contiguous()
         self.register_buffer("codebooks", cb, persistent=False)                    # [32, 2048, 256]
         self.register_buffer("cb_norm", cb.pow(2).sum(-1).contiguous(), persistent=False)
+        if self.precision == "bf16":  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
+            hi = cb.to(torch.bfloat16)
+            self.register_buffer("cb_split", torch.stack([hi, (cb - hi.float()).to(torch.bfloat16)]).contiguous(), persistent=False)
         inv_freq = 1.0 / (10000.0 ** (torch.arange(0, HEAD_DIM, 2, dtype=torch.int64).float() / HEAD_DIM))  # HF/mimi:560-562
         self.register_buffer("inv_freq", inv_freq, persistent=False)
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
@@ -313,9 +316,16 @@ class Mimi(Codec):
         B, N, _ = emb.shape
         toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
         xs = ops.conv(self._semantic_in, emb)
+        xa = ops.conv(self._acoustic_in, emb) if K > 1 else None
+        if self.precision == "bf16":  # tcgen05 distance GEMM + exact fp32 re-score (same decisions as the fp32 kernel)
+            ops.rvq_encode_tc(xs.view(B * N, -1), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, K), 1, code_offset=0,
+                              stage0=0, metric=1)
+            if K > 1:
+                ops.rvq_encode_tc(xa.view(B * N, -1), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, K), K - 1,
+                                  code_offset=1, stage0=1, metric=1)
+            return toks
         ops.rvq_encode(xs.view(B * N, -1), self.codebooks[:1], self.cb_norm[:1], toks.view(B * N, K), 1, code_offset=0, metric=1)
         if K > 1:
-            xa = ops.conv(self._acoustic_in, emb)
             ops.rvq_encode(xa.view(B * N, -1), self.codebooks[1:], self.cb_norm[1:], toks.view(B * N, K), K - 1, code_offset=1, metric=1)
         return toks
 

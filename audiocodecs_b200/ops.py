@@ -286,16 +286,17 @@ def rvq_encode(x, codebooks, cb_norm, codes_out, stages, code_offset=0, metric=0
     return codes_out
 
 
-def rvq_encode_tc(x, cb_split, codebooks, cb_norm, codes_out, stages, code_offset=0, residual_out=None):
-    """tensor-core RVQ encode (EnCodec metric): x [rows, 128] fp32; cb_split [2, S, C, 128] bf16 (hi, lo planes)."""
+def rvq_encode_tc(x, cb_split, codebooks, cb_norm, codes_out, stages, code_offset=0, residual_out=None, stage0=0, metric=0):
+    """tensor-core RVQ encode: x [rows, D] fp32 (D = 128 / 256); cb_split [2, S, C, D] bf16 (hi, lo planes); stages
+    stage0 .. stage0+stages-1 of the stacked codebooks; metric 0 = EnCodec, 1 = Mimi (cdist)."""
     _need_cuda(x, cb_split, codebooks, cb_norm, codes_out)
     rows, D = x.shape
     assert x.is_contiguous() and codes_out.dtype == torch.int64 and codes_out.is_contiguous()
     assert cb_split.dtype == torch.bfloat16 and cb_split.is_contiguous() and cb_split.shape[1:] == codebooks.shape
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_rvq_encode_tc(_ptr(x), _ptr(cb_split), _ptr(codebooks), _ptr(cb_norm), _ptr(codes_out), _ptr(residual_out),
-                                           rows, D, codebooks.shape[1], stages, codebooks.shape[0], codes_out.shape[-1], code_offset,
-                                           _stream()), "ac_rvq_encode_tc")
+                                           rows, D, codebooks.shape[1], stages, stage0, codebooks.shape[0], codes_out.shape[-1],
+                                           code_offset, metric, _stream()), "ac_rvq_encode_tc")
     if _PROFILER:
         _PROFILER.end("rvq_encode_tc_kernel", t0, 2.0 * rows * D * codebooks.shape[1] * stages, 4.0 * x.numel() + 8.0 * rows * stages)
     return codes_out

@@ -111,16 +111,19 @@ typedef struct ac_lstm_tc_desc {
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
 
 /*
- * Residual VQ encode on tcgen05 tensor cores (EnCodec metric, dim 128, n_codes a multiple of 256 up to 1024), all stages
- * fused with the fp32 residual resident in shared memory.  Distance GEMM in error-compensated bf16
+ * Residual VQ encode on tcgen05 tensor cores (dim 128 or 256, n_codes a multiple of 128 in [256, 2048]), all stages fused,
+ * the fp32 residual of a 128-frame tile resident in tensor memory.  Distance GEMM in error-compensated bf16
  * (r_hi.E_hi + r_hi.E_lo + r_lo.E_hi, fp32 accumulate in TMEM), per-frame running top-2, exact fp32 re-score of the two
- * candidates with the reference formula and tie rule, in-place subtract.  Same outputs as ac_rvq_encode_f32 (metric 0).
- * cb_split_bf16: [2][stages_total][n_codes][dim] = bf16(E), bf16(E - bf16(E)); codebooks: the fp32 originals.
- * Replaces HF/encodec/modeling_encodec.py:364-369,424-438.
+ * candidates with the reference formula and tie rule (metric 0: EnCodec, metric 1: Mimi cdist), in-place subtract.
+ * Same outputs as ac_rvq_encode_f32.  Stages stage0 .. stage0+stages-1 of the stacked codebooks are used:
+ * cb_split_bf16 [2][stages_total][n_codes][dim] = bf16(E), bf16(E - bf16(E)); codebooks [stages_total][n_codes][dim] fp32;
+ * cb_norm [stages_total][n_codes].  Codes are written at codes_out[row*code_stride + code_offset + k], k < stages.
+ * Replaces HF/encodec/modeling_encodec.py:364-369,424-438 and HF/mimi/modeling_mimi.py:1197-1202,1262-1280.
  */
 AC_API int ac_rvq_encode_tc(const float* x, const void* cb_split_bf16, const float* codebooks, const float* cb_norm,
                             int64_t* codes_out, float* residual_out, int64_t rows, int32_t dim, int32_t n_codes,
-                            int32_t stages, int32_t stages_total, int32_t code_stride, int32_t code_offset, void* stream);
+                            int32_t stages, int32_t stage0, int32_t stages_total, int32_t code_stride, int32_t code_offset,
+                            int32_t metric, void* stream);
 
 /*
  * Residual VQ encode, all stages fused (fp32): for k < stages: idx = argmin_c ||r - E_k[c]||^2

@@ -59,3 +59,26 @@ def test_mimi_end_to_end_code_match_report(mimi_sd, dev):
     assert per_stage[0] > 0.7 and min(per_stage) > 0.3
     rec = codec(sig.to(dev))
     assert tuple(rec.shape) == (2, 48000) and torch.isfinite(rec).all()
+
+
+def test_mimi_rvq_tensor_core_matches_fp32_kernel(mimi_sd, dev):
+    """Mimi's RVQ (dim 256, 2048 codes, cdist metric, semantic + acoustic chains) on the tcgen05 kernel makes the same
+    decisions as the exact fp32 SIMT kernel on the same projected embeddings (both re-score their candidates in fp32)."""
+    from audiocodecs_b200 import ops
+    codec = _codec(mimi_sd, dev, num_codebooks=32)
+    sig = make_input(77, 3, 30000).to(dev)
+    emb = codec.sig_to_feats(sig)                      # [B, N, 512]
+    B, N, _ = emb.shape
+    xa = ops.conv(codec._acoustic_in, emb).view(B * N, -1).contiguous()   # [rows, 256]
+    t_tc = torch.full((B * N, 31), -1, device=dev, dtype=torch.int64)
+    t_f32 = torch.empty_like(t_tc)
+    r_tc = torch.empty_like(xa)
+    r_f32 = torch.empty_like(xa)
+    ops.rvq_encode_tc(xa, codec.cb_split, codec.codebooks, codec.cb_norm, t_tc, 31, stage0=1, metric=1, residual_out=r_tc)
+    ops.rvq_encode(xa, codec.codebooks[1:], codec.cb_norm[1:], t_f32, 31, metric=1, residual_out=r_f32)
+    agree = (t_tc == t_f32).float().mean().item()
+    print(f"Mimi RVQ tensor-core vs fp32 kernel: {agree:.5f} of {t_tc.numel()} decisions agree")
+    assert int(t_tc.min()) >= 0 and int(t_tc.max()) < 2048
+    assert agree > 0.995, agree
+    same = (t_tc == t_f32).all(-1)
+    assert torch.allclose(r_tc[same], r_f32[same], atol=1e-5)
