@@ -166,6 +166,8 @@ class DAC(Codec):
                 p = f"decoder.block.{i}"
                 self._tdec.append((self._alpha(sd, p + ".snake1"), self._tcw_convtr(sd, p + ".conv_t1", s), s, self._tc_units(sd, p)))
             self._tdec_last_alpha = self._alpha(sd, "decoder.snake1")
+            self._tdec_last = tc.last_conv_weights(self._dec[-1])  # Cout = 1: row 0 of a 16-row tile (COL0 epilogue)
+            self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
     def _split(self, C):
@@ -253,7 +255,8 @@ class DAC(Codec):
             nxt = self._tdec[bi + 1][0] if bi + 1 < len(self._tdec) else self._tdec_last_alpha
             xs = self._tc_run_units(units, x, us, nxt)
             L = Lout
-        return ops.conv_last_bf16(self._dec[-1], xs, epi=EPI_TANH)
+        # last layer (Cout = 1, k7, zero padding 3, tanh) on the tap-GEMM kernel: column 0 of a 16-column tile
+        return tc.conv_last_tc(self._tdec_last, xs, 7, shift=-3, tanh=True)
 
     # ------------------------------------------------------------------ pieces
     def _stack(self, layers, x):

@@ -176,6 +176,8 @@ class Mimi(Codec):
                 self._tdec.append((self._tw_convtr(sd, f"decoder.layers.{idx}.conv", r), self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.1.conv"),
                                    self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.3.conv"), r))
                 idx += 3
+            self._tdec_last = tc.last_conv_weights(self._dec[-1])  # Cout = 1: row 0 of a 16-row tile (COL0 epilogue)
+            self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
     def _tc_resblock(self, Wk3, Wk1, x, xe, ye):
@@ -260,7 +262,7 @@ class Mimi(Codec):
             ye = Act(B, Lout, C, dev, split=sp)
             self._tc_resblock(Wk3, Wk1, x, xe, ye)
             L = Lout
-        return ops.conv_last_bf16(self._dec[-1], ye)
+        return tc.conv_last_tc(self._tdec_last, ye, self._dec[-1].taps, shift=-(self._dec[-1].taps - 1))
 
     # ------------------------------------------------------------------ pieces
     def _seanet(self, layers, x):

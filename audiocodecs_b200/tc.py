@@ -139,7 +139,8 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
         assert res is None and res32.is_contiguous() and res32.dtype == torch.float32 and res32[0].numel() == out_rows * out_ch
         d.res32, d.res_bstride = res32.data_ptr(), res32.stride(0)
     if y32 is not None:
-        assert y32.is_contiguous() and y32.dtype == torch.float32 and y32.shape[0] == B and y32[0].numel() == out_rows * out_ch
+        col0 = epi in (ops.EPI_COL0, ops.EPI_COL0_TANH)  # one real output channel: y32 is [B, out_rows]
+        assert y32.is_contiguous() and y32.dtype == torch.float32 and y32.shape[0] == B and y32[0].numel() == out_rows * (1 if col0 else out_ch)
         d.y32, d.y32_bstride = y32.data_ptr(), y32.stride(0)
     d.act, d.epi, d.act_mod = act, epi, act_mod or out_ch
     d.batch, d.m_rows, d.n_tile_hint, d.grid_hint = B, m_rows, n_tile_hint, grid_hint
@@ -244,3 +245,23 @@ def autotune(key, variants):
         if vname == name:
             return fn()
     raise KeyError(name)
+
+
+def last_conv_weights(spec):
+    """Cout = 1 last layer (ops.ConvSpec, w [taps][cin][1]) -> a 16-row weight matrix whose row 0 is the filter: the layer
+    runs on ac_conv_tc with the COL0 epilogue (the edge SIMT kernel was shared-memory-instruction bound at 1.4 TB/s)."""
+    taps, cin, _ = spec.w.shape
+    w = torch.zeros((16, taps * cin), dtype=torch.float32, device=spec.w.device)
+    w[0] = spec.w[:, :, 0].reshape(-1)
+    bias = torch.zeros(16, dtype=torch.float32, device=spec.w.device)
+    if spec.bias is not None:
+        bias[0] = spec.bias.reshape(-1)[0]
+    return TcWeights(w, bias)
+
+
+def conv_last_tc(W: TcWeights, x_act: Act, taps, *, origin=0, shift=0, rows=None, tanh=False, name="conv_last_tc"):
+    """x_act [B, T, C] (already activated, halo / out-of-bounds rows provide the padding) -> waveform [B, T] fp32."""
+    out = torch.empty((x_act.B, x_act.L), device=x_act.buf.device, dtype=torch.float32)
+    conv_tc(W, [Src(x_act, taps=taps, origin=origin, shift=shift, rows=rows)], x_act.L, y32=out,
+            epi=ops.EPI_COL0_TANH if tanh else ops.EPI_COL0, name=name)
+    return out
