@@ -35,6 +35,7 @@ class Mimi(Codec):
         self.vocab_size = 2048
         self.latent = latent
         self.precision = precision
+        self._rope_cache = {}
         self.compute_dtype = "bf16" if precision == "bf16" else "f32"
         if state_dict is None:
             try:
@@ -203,21 +204,29 @@ class Mimi(Codec):
 
     def _tc_transformer(self, layers, tws, h):
         """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,
-        fp32 accumulate, residual added in fp32 in the epilogue); LayerNorm and the 250-token attention stay fp32 SIMT."""
+        fp32 accumulate, residual added in fp32 in the epilogue) and so does the attention (ops.attention_tc); LayerNorm is
+        fp32 SIMT."""
         B, T, C = h.shape
         dev = h.device
         xa = Act(B, T, C, dev, split=True)
         fa = Act(B, T, 4 * C, dev, split=True)
         qkv = torch.empty((B, T, 3 * C), device=dev, dtype=torch.float32)
+        rope = self._rope_table(T, dev)
         for (ln, *_), (Wqkv, Wo, Wfc1, Wfc2) in zip(layers, tws):
             ops.f32_to_act(ops.layernorm(h, getattr(self, ln[0]), getattr(self, ln[1])), xa)
             tc.conv_tc(Wqkv, [Src(xa)], T, y32=qkv, name="tr_qkv_tc")
-            ops.f32_to_act(ops.attention(qkv, self.inv_freq, HEADS, HEAD_DIM, WINDOW), xa)
+            ops.attention_tc(qkv, rope, HEADS, HEAD_DIM, WINDOW, out_act=xa)
             tc.conv_tc(Wo, [Src(xa)], T, res32=h, y32=h, name="tr_o_tc")
             ops.f32_to_act(ops.layernorm(h, getattr(self, ln[2]), getattr(self, ln[3])), xa)
             tc.conv_tc(Wfc1, [Src(xa)], T, y=fa, epi=EPI_GELU, name="tr_fc1_tc")
             tc.conv_tc(Wfc2, [Src(fa)], T, res32=h, y32=h, name="tr_fc2_tc")
         return h
+
+    def _rope_table(self, T, dev):
+        key = (T, str(dev))
+        if key not in self._rope_cache:
+            self._rope_cache = {key: ops.rope_table(self.inv_freq, T)}  # one entry: the table of the last sequence length
+        return self._rope_cache[key]
 
     def _encoder_tc(self, sig):
         B, T = sig.shape

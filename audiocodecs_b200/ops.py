@@ -383,6 +383,38 @@ def attention(qkv, inv_freq, heads, head_dim, window):
     return out
 
 
+def rope_table(inv_freq, T):
+    """[T, 2*len(inv_freq)] fp32: cos | sin of position * inv_freq (HF/mimi:515-558)."""
+    _need_cuda(inv_freq)
+    half = inv_freq.numel()
+    table = torch.empty((T, 2 * half), device=inv_freq.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ac_rope_table_f32(_ptr(inv_freq), _ptr(table), T, half, _stream()), "ac_rope_table_f32")
+    return table
+
+
+def attention_tc(qkv, rope, heads, head_dim, window, out_act=None, out32=False):
+    """qkv [B,T,3*H*D] fp32 -> tc.Act `out_act` (split bf16) and/or a new fp32 [B,T,H*D]; RoPE + causal sliding-window
+    softmax attention on tcgen05 (split-bf16 products, fp32 softmax)."""
+    _need_cuda(qkv, rope)
+    B, T, _ = qkv.shape
+    assert qkv.is_contiguous() and qkv.dtype == torch.float32 and qkv.shape[2] == 3 * heads * head_dim
+    assert rope.shape == (T, head_dim) and rope.is_contiguous()
+    assert out_act is not None or out32
+    o32 = torch.empty((B, T, heads * head_dim), device=qkv.device, dtype=torch.float32) if out32 else None
+    vp = lambda v: ctypes.c_void_p(v) if v is not None else None
+    hi = lo = None
+    bs = 0
+    if out_act is not None:
+        assert (out_act.B, out_act.L, out_act.C) == (B, T, heads * head_dim)
+        hi, lo, bs = out_act.row_ptr(0), out_act.lo_ptr(0), out_act.bstride
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_attention_tc(_ptr(qkv), _ptr(rope), _ptr(o32), vp(hi), vp(lo), bs, B, T, heads, head_dim, window,
+                                          1.0 / math.sqrt(head_dim), _stream()), "ac_attention_tc")
+    if _PROFILER:
+        _PROFILER.end("attention_tc_kernel", t0, 4.0 * B * heads * head_dim * T * min(T, window) / 2, 4.0 * qkv.numel() + 4.0 * B * T * heads * head_dim)
+    return o32
+
+
 def upsample_dw(x, w):
     """x [B,L,C] fp32, w [C,4] -> [B,2L,C] (depthwise ConvTranspose1d k4 s2, causal trim)."""
     _need_cuda(x, w)

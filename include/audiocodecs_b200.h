@@ -312,6 +312,17 @@ AC_API int ac_attention_f32(const float* qkv, const float* inv_freq, float* out,
 AC_API int ac_upsample_dw_f32(const float* x, const float* w, float* y, int32_t batch, int32_t L, int32_t C, void* stream);
 
 /*
+ * The same attention (HF/mimi/modeling_mimi.py:645-736, mask :1096-1102) on tcgen05 tensor cores for the bf16 tensor path:
+ * Q K^T and P V as split-bf16 products (hi*hi + lo*hi + hi*lo, fp32 accumulate in tensor memory), online softmax in fp32.
+ * `rope` is the [T][head_dim] table cos | sin of positions 0..T-1 (ac_rope_table_f32 builds it from inv_freq,
+ * HF/mimi:515-558).  Output: fp32 [B][T][H*D] (out32) and/or split-bf16 planes out_hi [+ out_lo] with batch stride
+ * out_bstride (elements) -- the activation layout the output-projection GEMM reads.  No window limit.
+ */
+AC_API int ac_rope_table_f32(const float* inv_freq, float* table, int32_t T, int32_t half, void* stream);
+AC_API int ac_attention_tc(const float* qkv, const float* rope, float* out32, void* out_hi, void* out_lo, int64_t out_bstride,
+                           int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, void* stream);
+
+/*
  * DAC residual VQ (hidden 1024, codebook dim 8), all stages fused, fp32.
  * encode: z [rows][1024]; w_in [S][8][1024], b_in [S][8], codebooks [S][n_codes][8], w_out [S][1024][8], b_out [S][1024];
  *         codes int64 at codes[row*code_stride + k]; zq_out (optional) [rows][1024] = sum_k out_proj_k(.) (the

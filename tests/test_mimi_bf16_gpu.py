@@ -82,3 +82,46 @@ def test_mimi_rvq_tensor_core_matches_fp32_kernel(mimi_sd, dev):
     assert agree > 0.995, agree
     same = (t_tc == t_f32).all(-1)
     assert torch.allclose(r_tc[same], r_f32[same], atol=1e-5)
+
+
+def _attention_f64(qkv, window):
+    """The attention step of oracle.mimi_ref.transformer (HF/mimi:645-736, mask :1096-1102) in float64."""
+    B, T, _ = qkv.shape
+    H, Dh = mimi_ref.HEADS, mimi_ref.HEAD_DIM
+    cos, sin = (t.double() for t in mimi_ref.rope_tables(T))
+    q, k, v = (t.double().view(B, T, H, Dh).transpose(1, 2) for t in qkv.split(H * Dh, dim=-1))
+    q = q * cos + mimi_ref.rotate_half(q) * sin
+    k = k * cos + mimi_ref.rotate_half(k) * sin
+    i = torch.arange(T)
+    allowed = (i[None, :] <= i[:, None]) & (i[None, :] > i[:, None] - window)
+    s = (q @ k.transpose(2, 3)) / Dh ** 0.5
+    att = torch.softmax(s.masked_fill(~allowed, float("-inf")), dim=-1)
+    return (att @ v).transpose(1, 2).reshape(B, T, H * Dh)
+
+
+@pytest.mark.parametrize("B,T,window,scale", [(2, 250, 250, 1.0), (1, 700, 250, 3.0), (3, 1, 250, 1.0), (2, 129, 37, 8.0),
+                                              (1, 64, 250, 1.0), (2, 391, 128, 0.2)])
+def test_attention_tc_vs_f64(mimi_sd, dev, B, T, window, scale):
+    """tcgen05 attention (split-bf16 products, fp32 online softmax) vs float64 and vs the exact fp32 SIMT kernel: block
+    boundaries, windows shorter / longer than a key block, a single token, large logits (peaked softmax)."""
+    from audiocodecs_b200 import ops
+    from audiocodecs_b200.tc import Act
+    H, Dh = mimi_ref.HEADS, mimi_ref.HEAD_DIM
+    qkv = torch.randn(B, T, 3 * H * Dh, generator=torch.Generator().manual_seed(T)) * scale
+    ref = _attention_f64(qkv, window)
+    inv_freq = (1.0 / (10000.0 ** (torch.arange(0, Dh, 2, dtype=torch.int64).float() / Dh))).to(dev)
+    rope = ops.rope_table(inv_freq, T)
+    cos, sin = mimi_ref.rope_tables(T)
+    assert (rope.cpu() - torch.cat((cos[:, : Dh // 2], sin[:, : Dh // 2]), dim=1)).abs().max().item() < 2e-6
+    act = Act(B, T, H * Dh, dev, split=True)
+    got32 = ops.attention_tc(qkv.to(dev), rope, H, Dh, window, out_act=act, out32=True).cpu().double()
+    err = (got32 - ref).abs().max().item() / ref.abs().max().item()
+    print(f"attention_tc B={B} T={T} window={window}: max-abs err / max {err:.2e}")
+    # the lo*lo product is dropped: logits carry ~2^-17 of |q||k|, so the bound grows with the logit scale
+    tol = 2e-5 * max(1.0, scale * scale)
+    assert torch.isfinite(got32).all() and err < tol, err
+    planes = act.buf[:, act.hl:act.hl + T].float() + act.lo[:, act.hl:act.hl + T].float()
+    assert (planes.cpu().double() - got32).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    if window <= 256:
+        simt = ops.attention(qkv.to(dev), inv_freq, H, Dh, window).cpu().double()
+        assert (simt - ref).abs().max().item() / ref.abs().max().item() < 2e-5
