@@ -169,6 +169,8 @@ class Mimi(Codec):
                 idx += 3
             self._tenc_last = self._tw_conv(sd, f"encoder.layers.{idx + 1}.conv")
             self._tenc_tr = self._tw_transformer(sd, "encoder_transformer")
+            w = packing.fold_weight_norm(sd, "downsample.conv")  # [512, 512, 4], no bias
+            self._tdown = self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd.get("downsample.conv.bias"))
         if self.mode != "encode":
             self._tdec_tr = self._tw_transformer(sd, "decoder_transformer")
             self._tdec_first = self._tw_conv(sd, "decoder.layers.0.conv")
@@ -296,7 +298,17 @@ class Mimi(Codec):
     def _embeddings(self, sig):
         """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
         if self.precision == "bf16":
-            x = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
+            h = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
+            # `downsample` (HF/mimi:1419-1431): k4 s2 causal conv, replicate padding 2 left (+1 right for an odd length), as a
+            # 2-tap GEMM over the 2-phase view of the padded split-bf16 copy; fp32 out
+            B, L, C = h.shape
+            N = -(-L // 2)
+            ha = Act(B, L, C, h.device, hl=2, hr=2 * N - L, split=True)
+            ops.f32_to_act(h, ha)
+            ha.fill_halo(PAD_REPLICATE)
+            emb = torch.empty((B, N, C), device=h.device, dtype=torch.float32)
+            tc.conv_tc(self._tdown, [Src(ha, taps=2, origin=-2, phases=2, rows=N + 1)], N, y32=emb, name="downsample_tc")
+            return emb
         else:
             x = self._seanet(self._enc, sig.contiguous()[:, :, None])
             x = self._run_transformer(self._enc_tr, x)
