@@ -103,6 +103,7 @@ def lib():
         L.ac_rope_table_f32.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp]
         L.ac_attention_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp]
         L.ac_dac_rvq_encode_f32.argtypes = [c_vp] * 8 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_dac_rvq_encode_proj_f32.argtypes = [c_vp, c_i32] + [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_dac_rvq_decode_f32.argtypes = [c_vp] * 5 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_first_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_i32, c_i32, c_vp]

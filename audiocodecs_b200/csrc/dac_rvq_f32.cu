@@ -113,30 +113,132 @@ dac_rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ w_i
     }
 }
 
-// from_codes: out[row][c] = sum_k (b_out[k][c] + sum_d Wo[k][c][d] * cb[k][code][d]), accumulated in stage order from 0
-__global__ void dac_rvq_decode_kernel(const int64_t* __restrict__ codes, const float* __restrict__ cb, const float* __restrict__ w_out,
-                                      const float* __restrict__ b_out, float* __restrict__ out, int64_t rows, int n_codes,
-                                      int stages, int code_stride, int* err_flag) {
-    __shared__ float zp[16][CD];
-    const int64_t row = blockIdx.x;
+// from_codes: out[row][c] = sum_k (b_out[k][c] + sum_d Wo[k][c][d] * cb[k][code][d]), accumulated in stage order from 0.
+// A [rows x 8K] x [8K x 1024] GEMM with gathered rows: a CTA takes DR rows x 256 channels; the rows' code vectors sit in
+// shared memory (read as broadcasts), thread c keeps the DR running sums in registers and streams its 8 weights per stage
+// once per CTA instead of once per row (the first version re-read the 288 KB out_proj tensor for every row: 16 GB of
+// L2 traffic at 55 104 rows).  The per-element arithmetic (fma order d = 0..7 from the bias, stage sums added in order) is
+// unchanged, so the result is bit-identical to it.
+constexpr int DR = 32;
+__global__ void __launch_bounds__(256)
+dac_rvq_decode_kernel(const int64_t* __restrict__ codes, const float* __restrict__ cb, const float* __restrict__ w_out,
+                      const float* __restrict__ b_out, float* __restrict__ out, int64_t rows, int n_codes, int stages,
+                      int code_stride, int* err_flag) {
+    extern __shared__ __align__(16) float zp[];  // [DR][stages][CD]
+    const int64_t row0 = (int64_t)blockIdx.y * DR;
     const int tid = threadIdx.x;
-    if (tid < stages * CD) {
-        const int k = tid / CD, d = tid % CD;
-        int64_t c = codes[row * code_stride + k];
-        if (c < 0 || c >= n_codes) { if (err_flag) atomicExch(err_flag, 1); c = 0; }
-        zp[k][d] = cb[((size_t)k * n_codes + c) * CD + d];
+    const int c = blockIdx.x * 256 + tid;
+    for (int e = tid; e < DR * stages; e += 256) {
+        const int r = e / stages, k = e % stages;
+        float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
+        if (row0 + r < rows) {
+            int64_t code = codes[(row0 + r) * code_stride + k];
+            if (code < 0 || code >= n_codes) { if (err_flag) atomicExch(err_flag, 1); code = 0; }
+            const float4* src = reinterpret_cast<const float4*>(cb + ((size_t)k * n_codes + code) * CD);
+            lo4 = __ldg(src); hi4 = __ldg(src + 1);
+        }
+        reinterpret_cast<float4*>(zp)[e * 2] = lo4;
+        reinterpret_cast<float4*>(zp)[e * 2 + 1] = hi4;
     }
     __syncthreads();
-    for (int c = tid; c < HD; c += blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < stages; ++k) {
-            float o = __ldg(b_out + (size_t)k * HD + c);
-            const float* Wo = w_out + ((size_t)k * HD + c) * CD;
+    float acc[DR];
 #pragma unroll
-            for (int d = 0; d < CD; ++d) o = fmaf(__ldg(Wo + d), zp[k][d], o);
-            acc += o;
+    for (int r = 0; r < DR; ++r) acc[r] = 0.f;
+    for (int k = 0; k < stages; ++k) {
+        const float bias = __ldg(b_out + (size_t)k * HD + c);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_out + ((size_t)k * HD + c) * CD));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_out + ((size_t)k * HD + c) * CD) + 1);
+#pragma unroll
+        for (int r = 0; r < DR; ++r) {
+            const float4 a = reinterpret_cast<const float4*>(zp)[(r * stages + k) * 2];
+            const float4 b = reinterpret_cast<const float4*>(zp)[(r * stages + k) * 2 + 1];
+            float o = bias;
+            o = fmaf(w0.x, a.x, o); o = fmaf(w0.y, a.y, o); o = fmaf(w0.z, a.z, o); o = fmaf(w0.w, a.w, o);
+            o = fmaf(w1.x, b.x, o); o = fmaf(w1.y, b.y, o); o = fmaf(w1.z, b.z, o); o = fmaf(w1.w, b.w, o);
+            acc[r] += o;
         }
-        out[row * HD + c] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < DR; ++r)
+        if (row0 + r < rows) out[(row0 + r) * HD + c] = acc[r];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encode from PROJECTED latents (the bf16 tensor path).  in_proj is linear, so the 1024-wide residual never has to exist:
+//   z_e[k] = in_proj_k(z - sum_{j<k} out_j) = P[k] + c[k] - sum_{j<k} M[k][j] zq[j]
+// with P = all stages' in_proj of z at once (one [rows x 1024] x [1024 x 8S] tensor-core GEMM, bias included),
+// M[k][j] = W_in_k W_out_j (8x8), c[k] = -sum_{j<k} W_in_k b_out_j, zq[j] the straight-through value of stage j.
+// What remains per row is 8-dimensional: a warp takes 4 rows (lane = row r, dim d), scans the L2-normalised codebook
+// with lane = code (each code's 32 bytes are read once for the 4 rows), keeps the reference's score formula
+// -(|a|^2 - 2 a.b) + |b|^2 (HF/dac:165), first-index tie-break and STE arithmetic z_e + (z_q - z_e).
+// The sums are associated differently from the 1024-wide chain, so this path is used where the latents are already
+// approximate (precision="bf16"); the exact-order kernel above stays the fp32 path.
+constexpr int PW = 8, RPW = 4;  // warps per CTA, rows per warp
+__global__ void __launch_bounds__(PW * 32)
+dac_rvq_encode_proj_kernel(const float* __restrict__ P, int ldp, const float* __restrict__ cconst, const float* __restrict__ M,
+                           const float* __restrict__ cbn, const float* __restrict__ cbn2, const float* __restrict__ cb,
+                           int64_t* __restrict__ codes, int64_t rows, int n_codes, int stages, int stages_total, int code_stride) {
+    extern __shared__ __align__(16) float zq_s[];  // [PW][stages][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 3, d = lane & 7;
+    const int64_t row = ((int64_t)blockIdx.x * PW + warp) * RPW + r;
+    const bool live = row < rows;
+    float* zq_w = zq_s + (size_t)warp * stages * 32;
+    for (int k = 0; k < stages; ++k) {
+        float ze = (live ? __ldg(P + row * ldp + k * CD + d) : 0.f) + __ldg(cconst + k * CD + d);
+        for (int j = 0; j < k; ++j) {
+            const float* m = M + (((size_t)k * stages_total + j) * CD + d) * CD;
+            const float* q = zq_w + j * 32 + (lane & ~7);
+#pragma unroll
+            for (int e = 0; e < CD; ++e) ze = fmaf(-__ldg(m + e), q[e], ze);
+        }
+        float n = ze * ze;
+        n += __shfl_xor_sync(0xffffffffu, n, 1); n += __shfl_xor_sync(0xffffffffu, n, 2); n += __shfl_xor_sync(0xffffffffu, n, 4);
+        const float a = ze * (1.0f / fmaxf(sqrtf(n), 1e-12f));  // F.normalize
+        float an = a * a;
+        an += __shfl_xor_sync(0xffffffffu, an, 1); an += __shfl_xor_sync(0xffffffffu, an, 2); an += __shfl_xor_sync(0xffffffffu, an, 4);
+        float av[RPW][CD], anv[RPW], bv[RPW];
+        int bi[RPW];
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+#pragma unroll
+            for (int dd = 0; dd < CD; ++dd) av[rr][dd] = __shfl_sync(0xffffffffu, a, rr * 8 + dd);
+            anv[rr] = __shfl_sync(0xffffffffu, an, rr * 8);
+            bv[rr] = -INFINITY;
+            bi[rr] = 0x7fffffff;
+        }
+        const float* Cn = cbn + (size_t)k * n_codes * CD;
+        for (int c = lane; c < n_codes; c += 32) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(Cn + (size_t)c * CD));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(Cn + (size_t)c * CD) + 1);
+            const float bn2 = __ldg(cbn2 + (size_t)k * n_codes + c);
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                float dot = 0.f;
+                dot = fmaf(av[rr][0], b0.x, dot); dot = fmaf(av[rr][1], b0.y, dot); dot = fmaf(av[rr][2], b0.z, dot);
+                dot = fmaf(av[rr][3], b0.w, dot); dot = fmaf(av[rr][4], b1.x, dot); dot = fmaf(av[rr][5], b1.y, dot);
+                dot = fmaf(av[rr][6], b1.z, dot); dot = fmaf(av[rr][7], b1.w, dot);
+                const float score = -(anv[rr] - 2.f * dot) + bn2;
+                if (score > bv[rr]) { bv[rr] = score; bi[rr] = c; }  // ascending c per lane: strict > keeps the first index
+            }
+        }
+        int mine = 0;
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[rr], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[rr], o);
+                if (ov > bv[rr] || (ov == bv[rr] && oi < bi[rr])) { bv[rr] = ov; bi[rr] = oi; }
+            }
+            if (rr == r) mine = bi[rr];
+        }
+        if (mine >= n_codes) mine = 0;  // all-NaN scores: keep the gather in range
+        const float zq = __ldg(cb + ((size_t)k * n_codes + mine) * CD + d);
+        __syncwarp();
+        zq_w[k * 32 + lane] = ze + (zq - ze);  // straight-through arithmetic kept in eval
+        __syncwarp();
+        if (live && d == 0) codes[row * code_stride + k] = (int64_t)mine;
     }
 }
 
@@ -167,7 +269,22 @@ extern "C" int ac_dac_rvq_decode_f32(const int64_t* codes, const float* codebook
     AC_REQUIRE(codes && codebooks && w_out && b_out && out, "ac_dac_rvq_decode_f32: null pointer");
     AC_REQUIRE(hidden == HD && cb_dim == CD, "ac_dac_rvq_decode_f32: built for hidden %d / codebook dim %d", HD, CD);
     AC_REQUIRE(rows > 0 && stages > 0 && stages <= 16, "ac_dac_rvq_decode_f32: bad sizes");
-    dac_rvq_decode_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(codes, codebooks, w_out, b_out, out, rows, n_codes,
-                                                                             stages, code_stride, err_flag);
+    AC_REQUIRE((rows + DR - 1) / DR <= 65535, "ac_dac_rvq_decode_f32: too many rows for one launch");
+    dac_rvq_decode_kernel<<<dim3(HD / 256, (unsigned)((rows + DR - 1) / DR)), 256, (size_t)DR * stages * CD * 4, (cudaStream_t)stream>>>(
+        codes, codebooks, w_out, b_out, out, rows, n_codes, stages, code_stride, err_flag);
     return ac::finish_launch("ac_dac_rvq_decode_f32");
+}
+
+extern "C" int ac_dac_rvq_encode_proj_f32(const float* proj, int32_t ld_proj, const float* cconst, const float* cross,
+                                          const float* cb_normed, const float* cb_norm2, const float* codebooks, int64_t* codes,
+                                          int64_t rows, int32_t cb_dim, int32_t n_codes, int32_t stages, int32_t stages_total,
+                                          int32_t code_stride, void* stream) {
+    AC_REQUIRE(proj && cconst && cross && cb_normed && cb_norm2 && codebooks && codes, "ac_dac_rvq_encode_proj_f32: null pointer");
+    AC_REQUIRE(cb_dim == CD, "ac_dac_rvq_encode_proj_f32: built for codebook dim %d", CD);
+    AC_REQUIRE(rows > 0 && stages > 0 && stages <= stages_total && stages_total <= 32 && n_codes > 0 && ld_proj >= stages * CD,
+               "ac_dac_rvq_encode_proj_f32: bad sizes");
+    const int64_t per_cta = PW * RPW;
+    dac_rvq_encode_proj_kernel<<<(unsigned)((rows + per_cta - 1) / per_cta), PW * 32, (size_t)PW * stages * 32 * 4, (cudaStream_t)stream>>>(
+        proj, ld_proj, cconst, cross, cb_normed, cb_norm2, codebooks, codes, rows, n_codes, stages, stages_total, code_stride);
+    return ac::finish_launch("ac_dac_rvq_encode_proj_f32");
 }

@@ -122,6 +122,8 @@ class DAC(Codec):
         self.register_buffer("b_out", stack(lambda p: sd[p + "out_proj.bias"].float()), persistent=False)
         self.register_buffer("codebooks", stack(lambda p: sd[p + "codebook.weight"].float()), persistent=False)                  # [S,1024,8]
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
+        if self.precision == "bf16" and self.mode != "decode":
+            self._build_rvq_proj()
 
     def _packed(self):
         return self._specs + self._tcw
@@ -134,6 +136,27 @@ class DAC(Codec):
         W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"])
         self._tcw.append(W)
         return W
+
+    def _build_rvq_proj(self):
+        """Constants of the projected RVQ encode (ops.dac_rvq_encode_proj): every stage's in_proj as one GEMM weight, and the
+        8x8 cross terms W_in_k W_out_j that replace the 1024-wide residual update (computed in float64)."""
+        S, D, H = self.w_in.shape
+        win, wout, bout = self.w_in.double(), self.w_out.double(), self.b_out.double()
+        n = -(-S * D // 16) * 16
+        w_all = torch.zeros(n, H, dtype=torch.float64)
+        w_all[: S * D] = win.reshape(S * D, H)
+        b_all = torch.zeros(n)
+        b_all[: S * D] = self.b_in.reshape(-1)
+        self._tproj = TcWeights(w_all.float(), b_all)
+        self._tcw.append(self._tproj)
+        cross = torch.einsum("kdc,jce->kjde", win, wout)                  # [S,S,8,8]
+        v = torch.einsum("kdc,jc->kjd", win, bout)                        # [S,S,8]
+        lower = torch.tril(torch.ones(S, S, dtype=torch.float64), -1)     # j < k
+        cb_n = torch.nn.functional.normalize(self.codebooks, dim=-1)      # eps 1e-12, as F.normalize in the reference
+        self.register_buffer("rvq_cross", cross.float().contiguous(), persistent=False)
+        self.register_buffer("rvq_cconst", (-(v * lower[:, :, None]).sum(1)).float().contiguous(), persistent=False)
+        self.register_buffer("cb_normed", cb_n.contiguous(), persistent=False)
+        self.register_buffer("cb_norm2", (cb_n * cb_n).sum(-1).contiguous(), persistent=False)
 
     def _tcw_convtr(self, sd, prefix, stride):
         w = packing.fold_weight_norm(sd, prefix)     # [Cin, Cout, 2s]
@@ -208,7 +231,7 @@ class DAC(Codec):
             x, xs = y, ys
         return xs
 
-    def _encoder_tc(self, sig):
+    def _encoder_tc(self, sig, proj=False):
         B, T = sig.shape
         dev = sig.device
         C = self._enc[0].cout
@@ -230,6 +253,12 @@ class DAC(Codec):
             tc.conv_tc(Wdown, [Src(ys, taps=2, origin=-p, phases=s, rows=(p + L + hr) // s)], Lout, y=x, y_act=xs, act=ACT_SNAKE,
                        alpha=nxt.t, name="down_tc")
             L = Lout
+        if proj:  # latents as a split-bf16 activation -> all RVQ stages' in_proj in one GEMM: [B, L, 8S (padded to 16)] fp32
+            za = Act(B, L, C, dev, split=True)
+            tc.conv_tc(self._tenc_last[1], [Src(xs, taps=3, shift=-1)], L, y=za, name="conv_k3_tc")
+            P = torch.empty((B, L, self._tproj.n_total), device=dev, dtype=torch.float32)
+            tc.conv_tc(self._tproj, [Src(za)], L, y32=P, name="rvq_in_proj_tc")
+            return P
         z = torch.empty((B, L, C), device=dev, dtype=torch.float32)
         tc.conv_tc(self._tenc_last[1], [Src(xs, taps=3, shift=-1)], L, y32=z, name="conv_k3_tc")
         return z
@@ -282,6 +311,10 @@ class DAC(Codec):
         return self._stack(self._enc, sig.contiguous()[:, :, None])
 
     def _sig_to_toks(self, sig, length):  # R/audiocodecs/dac.py:94-100 (`length` is ignored by the reference)
+        if self.precision == "bf16":  # 8-dimensional RVQ chain on the projected latents (no 1024-wide residual)
+            P = self._encoder_tc(sig.contiguous(), proj=True)
+            return ops.dac_rvq_encode_proj(P, self.rvq_cconst, self.rvq_cross, self.cb_normed, self.cb_norm2, self.codebooks,
+                                           self.num_codebooks)
         z = self._encode_latents(sig)
         return ops.dac_rvq_encode(z, self.w_in, self.b_in, self.codebooks, self.w_out, self.b_out, self.num_codebooks)
 

@@ -440,6 +440,21 @@ def dac_rvq_encode(z, w_in, b_in, cb, w_out, b_out, stages, want_zq=False):
     return (codes, zq) if want_zq else codes
 
 
+def dac_rvq_encode_proj(proj, cconst, cross, cb_normed, cb_norm2, cb, stages):
+    """proj [B,N,ld] fp32 (all stages' in_proj of z, bias included) -> codes [B,N,stages] int64."""
+    _need_cuda(proj, cross)
+    B, N, ld = proj.shape
+    assert proj.is_contiguous() and proj.dtype == torch.float32
+    codes = torch.empty((B, N, stages), device=proj.device, dtype=torch.int64)
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_dac_rvq_encode_proj_f32(_ptr(proj), ld, _ptr(cconst), _ptr(cross), _ptr(cb_normed), _ptr(cb_norm2), _ptr(cb),
+                                                     _ptr(codes), B * N, cb.shape[2], cb.shape[1], stages, cb.shape[0], stages,
+                                                     _stream()), "ac_dac_rvq_encode_proj_f32")
+    if _PROFILER:
+        _PROFILER.end("dac_rvq_encode_proj_kernel", t0, 2.0 * B * N * stages * 8 * cb.shape[1], 4.0 * proj.numel())
+    return codes
+
+
 def dac_rvq_decode(codes, cb, w_out, b_out, err_flag=None):
     """codes [B,N,K] int64 -> z [B,N,1024] fp32 (from_codes)."""
     _need_cuda(codes, cb)

@@ -335,6 +335,17 @@ AC_API int ac_dac_rvq_encode_f32(const float* z, const float* w_in, const float*
                                  const float* w_out, const float* b_out, int64_t* codes, float* zq_out, int64_t rows,
                                  int32_t hidden, int32_t cb_dim, int32_t n_codes, int32_t stages, int32_t code_stride,
                                  void* stream);
+/*
+ * Encode from projected latents (bf16 tensor path): proj [rows][ld_proj] = in_proj of ALL stages applied to z (bias included,
+ * column k*8+d); cconst [S][8] = -sum_{j<k} W_in_k b_out_j; cross [S][S][8][8] = W_in_k W_out_j (j<k used);
+ * cb_normed [S][n_codes][8] = L2-normalised codebooks, cb_norm2 [S][n_codes] their squared norms.  Same score formula,
+ * tie-break and straight-through arithmetic as ac_dac_rvq_encode_f32 (dac/nn/quantize.py @1.0.0, HF/dac:122-170), without
+ * ever forming the 1024-wide residual.
+ */
+AC_API int ac_dac_rvq_encode_proj_f32(const float* proj, int32_t ld_proj, const float* cconst, const float* cross,
+                                      const float* cb_normed, const float* cb_norm2, const float* codebooks, int64_t* codes,
+                                      int64_t rows, int32_t cb_dim, int32_t n_codes, int32_t stages, int32_t stages_total,
+                                      int32_t code_stride, void* stream);
 AC_API int ac_dac_rvq_decode_f32(const int64_t* codes, const float* codebooks, const float* w_out, const float* b_out,
                                  float* out, int64_t rows, int32_t hidden, int32_t cb_dim, int32_t n_codes, int32_t stages,
                                  int32_t code_stride, int32_t* err_flag, void* stream);

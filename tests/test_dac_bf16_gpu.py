@@ -61,3 +61,43 @@ def test_dac_end_to_end_code_match_report(dac_sd, dev):
     assert per_stage[0] > 0.8 and min(per_stage) > 0.4
     rec = codec(sig.to(dev))
     assert tuple(rec.shape) == (2, 44032) and torch.isfinite(rec).all()
+
+
+@pytest.mark.parametrize("B,N,K", [(2, 301, 9), (1, 5, 3), (3, 33, 1)])
+def test_dac_rvq_encode_projected_vs_oracle(dac_sd, dev, B, N, K):
+    """The 8-dimensional RVQ chain on projected latents (ac_dac_rvq_encode_proj_f32) must take the oracle's decisions on
+    identical latents: codes equal wherever the oracle's top-2 relative gap exceeds 1e-4 on every stage up to that one
+    (a flipped near-tie changes the residual of the later stages of that frame)."""
+    from audiocodecs_b200 import ops
+    codec = _codec(dac_sd, dev, num_codebooks=K)
+    z = torch.randn(B, 1024, N, generator=torch.Generator().manual_seed(N)) * 2.0
+    with torch.no_grad():
+        ref, gaps, _ = dac_ref.rvq_encode(dac_sd, z, K, return_gaps=True)      # [B,K,N]
+    S = codec.w_in.shape[0]
+    w_all = codec.w_in.double().reshape(S * 8, 1024).cpu()
+    P = torch.zeros(B, N, codec._tproj.n_total, dtype=torch.float64)
+    P[..., : S * 8] = z.double().permute(0, 2, 1) @ w_all.t() + codec.b_in.double().reshape(-1).cpu()
+    got = ops.dac_rvq_encode_proj(P.float().to(dev).contiguous(), codec.rvq_cconst, codec.rvq_cross, codec.cb_normed, codec.cb_norm2,
+                                  codec.codebooks, K).cpu()
+    assert got.dtype == torch.int64 and tuple(got.shape) == (B, N, K)
+    ref = ref.permute(0, 2, 1)
+    clear = (gaps.permute(0, 2, 1) > 1e-4).long().cumprod(dim=-1).bool()   # no near-tie at this or any earlier stage
+    eq = got == ref
+    print(f"DAC projected RVQ: {eq.float().mean().item():.4f} equal, {(~clear).float().mean().item():.4f} behind a near-tie")
+    assert eq[clear].all(), f"{(~eq[clear]).sum().item()} mismatches away from near-ties"
+    # and the exact-order kernel agrees with the oracle on the same latents
+    exact = ops.dac_rvq_encode(z.permute(0, 2, 1).contiguous().to(dev), codec.w_in, codec.b_in, codec.codebooks, codec.w_out,
+                               codec.b_out, K).cpu()
+    assert (exact == ref)[clear].all()
+
+
+def test_dac_rvq_decode_blocked_matches_oracle(dac_sd, dev):
+    """from_codes with 32-row blocks and ragged tails vs the oracle (fp32, same arithmetic order per element)."""
+    from audiocodecs_b200 import ops
+    codec = _codec(dac_sd, dev, num_codebooks=9)
+    for B, N, K in [(2, 77, 9), (1, 1, 9), (3, 32, 2)]:
+        toks = torch.randint(0, 1024, (B, N, K), generator=torch.Generator().manual_seed(N))
+        with torch.no_grad():
+            ref = dac_ref.from_codes(dac_sd, toks.permute(0, 2, 1)).permute(0, 2, 1)
+        got = ops.dac_rvq_decode(toks.to(dev), codec.codebooks[:K], codec.w_out[:K], codec.b_out[:K]).cpu()
+        assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
