@@ -162,7 +162,10 @@ class Encodec(Codec):
     def _tc_lstm(self, sd, prefix):
         out = []
         for l in range(2):
-            W = TcWeights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"])
+            # single bf16 product for the input projection: the recurrence (bf16 h, bf16 W_hh) dominates the LSTM's error, a
+            # split here changes the decoder SI-SNR by < 0.1 dB (measured: 45.1 -> 45.1 dB, code match unchanged)
+            W = TcWeights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"],
+                          split=False)
             self._tcw.append(W)
             out.append(W)
         return out
@@ -191,10 +194,10 @@ class Encodec(Codec):
         B, N, C = x.B, x.L, x.C
         dev = x.buf.device
         pre = torch.empty((B, N, 4 * C), device=dev, dtype=torch.float32)
-        tc.conv_tc(Ws[0], [Src(x)], N, y32=pre, name="lstm_ih_tc")
-        h0 = Act(B, N, C, dev, split=True)
+        tc.conv_tc(Ws[0], [Src(x.hi_only())], N, y32=pre, name="lstm_ih_tc")
+        h0 = Act(B, N, C, dev, split=True)   # the lo plane matters for the skip-add of the last layer's h only
         ops.lstm_tc(pre, getattr(self, whh[0] + "_bf16"), out=h0)
-        tc.conv_tc(Ws[1], [Src(h0)], N, y32=pre, name="lstm_ih_tc")
+        tc.conv_tc(Ws[1], [Src(h0.hi_only())], N, y32=pre, name="lstm_ih_tc")
         # the skip-add + ELU runs as its own HBM-bound pass: inside the recurrence kernel its loads/stores sat on the
         # per-step critical path (layer 1 took 3.8 ms against 2.4 ms for layer 0)
         ops.lstm_tc(pre, getattr(self, whh[1] + "_bf16"), out=h0)

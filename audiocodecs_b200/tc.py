@@ -46,6 +46,14 @@ class Act:
     def data(self):
         return self.buf[:, self.hl:self.hl + self.L]
 
+    def hi_only(self):
+        """the same buffer without its lo plane (a single-product operand)."""
+        if self.lo is None:
+            return self
+        v = Act.__new__(Act)
+        v.buf, v.lo, v.hl, v.hr, v.L, v.C = self.buf, None, self.hl, self.hr, self.L, self.C
+        return v
+
     def fill_halo(self, mode, reflect_len=0):
         if self.hl + self.hr == 0:
             return
