@@ -5,6 +5,8 @@ behaviour; the resampler is our polyphase FIR kernel instead of torchaudio.
 """
 from abc import ABC, abstractmethod
 
+import re
+
 import torch
 
 from . import ops
@@ -41,6 +43,15 @@ class Codec(torch.nn.Module, ABC):
         # the reference substitutes ones(B) here (R/codec.py:64-65); `None` carries the same meaning to the
         # hooks without spending kernels on an all-true padding mask
         return sig, length
+
+    # bf16 tensor path: layers whose weights are stored as ONE bf16 plane instead of the (hi, lo) pair -- one tensor-core
+    # product fewer per MAC where the measured SI-SNR margin allows it (regex over state-dict prefixes; None = no layer)
+    W_SINGLE = None
+
+    def _w_split(self, name):
+        pat = getattr(self, "w_single", None)
+        pat = self.W_SINGLE if pat is None else pat
+        return not (pat and re.search(pat, name))
 
     def _chunks(self, n_clips, samples_per_clip):
         per = max(1, int(self.max_chunk_samples // max(1, samples_per_clip)))

@@ -95,6 +95,28 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
     const bool has_res = p.res != nullptr, has_res_lo = p.res_lo != nullptr, has_res32 = p.res32 != nullptr;
     const bool periodic = p.act_mod < p.n_total;
     const bool wide = p.wide_ok != 0;  // bias / alpha are indexed by n % act_mod (transposed conv: n = phase*C + c)
+    const bool any_res = has_res || has_res32;
+    // The residual of an item (64 bytes per lane: bf16 hi + lo runs, or one fp32 run) is fetched ONE ITEM AHEAD -- the first
+    // item's before the wait on the accumulator -- so its DRAM latency runs under the MMAs / the previous item's math instead
+    // of stalling every item (ncu: long_scoreboard was the top stall of the residual-adding launches).
+    uint4 rnext[4] = {};
+    auto fetch_res = [&](int b, int mg, int nt, int g, int c) {
+        const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
+        const int n0 = nt * p.n_tile + c * 16;
+        const long long flat = (long long)m * p.n_total + n0 - p.out_shift;
+        if (!(m < p.m_rows && wide && flat >= 0 && flat + 16 <= p.out_valid && n0 + 16 <= p.n_total)) return;
+        if (has_res) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.res + (long long)b * p.res_bs + flat);
+            rnext[0] = r[0]; rnext[1] = r[1];
+            if (has_res_lo) {
+                const uint4* l = reinterpret_cast<const uint4*>(p.res_lo + (long long)b * p.res_bs + flat);
+                rnext[2] = l[0]; rnext[3] = l[1];
+            }
+        } else {
+            const uint4* r = reinterpret_cast<const uint4*>(p.res32 + (long long)b * p.res_bs + flat);
+            rnext[0] = r[0]; rnext[1] = r[1]; rnext[2] = r[2]; rnext[3] = r[3];
+        }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;
@@ -103,11 +125,12 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
         const int b = rest / p.m_groups;
         const int as = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+        int g = 0, c = slot;
+        while (c >= chunks_n) { c -= chunks_n; ++g; }
+        if (any_res && slot < items) fetch_res(b, mg, nt, g, c);
         mbar_wait(&tfull[as], tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.G * p.n_tile;
-        int g = 0, c = slot;
-        while (c >= chunks_n) { c -= chunks_n; ++g; }
         for (int item = slot; item < items; item += EPI_WARPS / 4) {
             uint32_t v[16];
             tmem_ld16(taddr + g * p.n_tile + c * 16, v);
@@ -119,6 +142,8 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
             if (periodic) ch0 = n0 % p.act_mod;
             c += EPI_WARPS / 4;
             while (c >= chunks_n) { c -= chunks_n; ++g; }
+            const uint4 rcur[4] = {rnext[0], rnext[1], rnext[2], rnext[3]};
+            if (any_res && item + EPI_WARPS / 4 < items) fetch_res(b, mg, nt, g, c);
             tmem_ld_wait();
             if (!ok) continue;
             if (p.epi >= AC_EPI_COL0) {
@@ -147,15 +172,14 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                     for (int i = 0; i < 16; ++i) o[i] = ac::gelu_erf(o[i]);
                 }
                 if (has_res) {
-                    add_bf16x16(o, p.res + (long long)b * p.res_bs + flat);
-                    if (has_res_lo) add_bf16x16(o, p.res_lo + (long long)b * p.res_bs + flat);
+                    add_bf16x16(o, rcur[0], rcur[1]);
+                    if (has_res_lo) add_bf16x16(o, rcur[2], rcur[3]);
                 }
                 if (has_res32) {
-                    const float4* r = reinterpret_cast<const float4*>(p.res32 + (long long)b * p.res_bs + flat);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 rr = r[q];
-                        o[4 * q] += rr.x; o[4 * q + 1] += rr.y; o[4 * q + 2] += rr.z; o[4 * q + 3] += rr.w;
+                        o[4 * q] += __uint_as_float(rcur[q].x); o[4 * q + 1] += __uint_as_float(rcur[q].y);
+                        o[4 * q + 2] += __uint_as_float(rcur[q].z); o[4 * q + 3] += __uint_as_float(rcur[q].w);
                     }
                 }
                 if (p.y32) {

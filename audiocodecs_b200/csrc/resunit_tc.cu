@@ -243,7 +243,10 @@ __device__ __forceinline__ void add_bias16(float (&o)[16], const uint32_t (&v)[1
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// RAW = false drops the four transform warps from the launch: 608 threads leave the epilogue a 104-register budget (room
+// for the one-item-ahead residual prefetch) instead of 88.
+template <bool RAW>
+__global__ void __launch_bounds__(RAW ? THREADS : THREADS - 32 * XF_WARPS, 1)
 resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ RuParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -297,20 +300,20 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-    for (int i = threadIdx.x; i < p.ch; i += THREADS) {
+    for (int i = threadIdx.x; i < p.ch; i += blockDim.x) {
         bias1_s[i] = p.bias1 ? p.bias1[i] : 0.f;
         const float a = p.act1 == AC_ACT_SNAKE ? p.alpha1[i] : 1.f;
         alpha1_s[i] = a;
         ralpha1_s[i] = 1.0f / (a + 1e-9f);
     }
-    for (int i = threadIdx.x; i < p.cout; i += THREADS) {
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) {
         bias2_s[i] = p.bias2 ? p.bias2[i] : 0.f;
         const float a = p.act2 == AC_ACT_SNAKE ? p.alpha2[i] : 1.f;
         alpha2_s[i] = a;
         ralpha2_s[i] = 1.0f / (a + 1e-9f);
     }
     if (p.raw)
-        for (int i = threadIdx.x; i < p.cin; i += THREADS) {
+        for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
             const float a = p.act0 == AC_ACT_SNAKE ? p.alpha0[i] : 1.f;
             alpha0_s[i] = a;
             ralpha0_s[i] = 1.0f / (a + 1e-9f);
@@ -424,7 +427,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         else if (ka == 1 && kh == 2) mma_role<1, 2>(AC_RU_ARGS);
         else mma_role<1, 1>(AC_RU_ARGS);
 #undef AC_RU_ARGS
-    } else if (warp >= FIRST_XF_WARP) {
+    } else if (RAW && warp >= FIRST_XF_WARP) {
         // ================================================================= transform warps (raw mode): block by block,
         // activated = act0(raw_hi [+ raw_lo]) written at the same (swizzled) offsets of the E ring; elementwise, so the
         // operand layout TMA produced is preserved.  Zero-filled (out-of-bounds) rows stay zero: ELU(0) = Snake(0) = 0.
@@ -541,29 +544,46 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             if (lane == 0) mbar_arrive(&h_ready[ab]);
         };
         // ---------------- epilogue 2: acc2 -> bias, residual, raw / activated outputs
+        // the skip input of an item (32 + 32 bytes per lane) is fetched one item ahead, the first item's before the wait on
+        // acc2: its DRAM latency runs under GEMM2 / the previous item's math (ncu: long_scoreboard was the top stall)
+        uint4 rnext[4] = {};
+        auto fetch_res = [&](int b, int mg, int g, int c) {
+            const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
+            if (m >= p.m_rows) return;
+            const long long off = (long long)b * p.res_bs + (long long)m * p.cout + c * 16;
+            const uint4* r = reinterpret_cast<const uint4*>(p.res + off);
+            rnext[0] = r[0]; rnext[1] = r[1];
+            if (has_res_lo) {
+                const uint4* l = reinterpret_cast<const uint4*>(p.res_lo + off);
+                rnext[2] = l[0]; rnext[3] = l[1];
+            }
+        };
         auto epi2 = [&](int it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int mg = tile % p.m_groups;
             const int b = tile / p.m_groups;
-            mbar_wait(acc2_full, it & 1);
-            tc_fence_after();
             int g = 0, c = slot;
             while (c >= c2) { c -= c2; ++g; }
+            if (has_res && slot < p.G * c2) fetch_res(b, mg, g, c);
+            mbar_wait(acc2_full, it & 1);
+            tc_fence_after();
             for (int item = slot; item < p.G * c2; item += EPI_WARPS / 4) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + p.acc2_col + g * p.cout + c * 16, v);
                 const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
                 const int col = c * 16;
                 const long long flat = (long long)m * p.cout + col;
-                tmem_ld_wait();
                 c += EPI_WARPS / 4;
                 while (c >= c2) { c -= c2; ++g; }
+                const uint4 rcur[4] = {rnext[0], rnext[1], rnext[2], rnext[3]};
+                if (has_res && item + EPI_WARPS / 4 < p.G * c2) fetch_res(b, mg, g, c);
+                tmem_ld_wait();
                 if (m >= p.m_rows) continue;
                 float o[16];
                 add_bias16(o, v, bias2_s + col);
                 if (has_res) {
-                    add_bf16x16(o, p.res + (long long)b * p.res_bs + flat);
-                    if (has_res_lo) add_bf16x16(o, p.res_lo + (long long)b * p.res_bs + flat);
+                    add_bf16x16(o, rcur[0], rcur[1]);
+                    if (has_res_lo) add_bf16x16(o, rcur[2], rcur[3]);
                 }
                 if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr);
                 if (p.y_act) {
@@ -768,7 +788,8 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     if (smem <= (size_t)SMEM_HALF + 1024) smem = SMEM_HALF + 2048;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(resunit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(resunit_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(resunit_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) { ac::set_error("ac_resunit_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
@@ -776,6 +797,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     long long grid = sms;
     if (d->grid_hint > 0) grid = d->grid_hint;
     if (total_tiles < grid) grid = total_tiles;
-    resunit_tc_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    if (p.raw) resunit_tc_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    else resunit_tc_kernel<false><<<(unsigned)grid, THREADS - 32 * XF_WARPS, smem, (cudaStream_t)stream>>>(maps, p);
     return ac::finish_launch("ac_resunit_tc");
 }

@@ -55,6 +55,16 @@ __device__ __forceinline__ void add_bf16x16(float (&o)[16], const __nv_bfloat16*
     }
 }
 
+__device__ __forceinline__ void add_bf16x16(float (&o)[16], const uint4& r0, const uint4& r1) {
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+        o[2 * i] += __low2float(h2);
+        o[2 * i + 1] += __high2float(h2);
+    }
+}
+
 // 16 values -> one 32-byte store of the bf16 roundings (+ one of the rounding residuals when `lo` is given)
 __device__ __forceinline__ void store_bf16x16(const float (&o)[16], __nv_bfloat16* hi, __nv_bfloat16* lo) {
     uint32_t q[8];

@@ -40,9 +40,15 @@ class DAC(Codec):
     def _hop(self):
         return 512
 
+    # single-plane weights for the k7 convolutions of the residual units (64 % of the FLOPs): decoder SI-SNR 47.0 -> 45.9 dB,
+    # end-to-end code match 99.8 -> 99.4 %, step 329 -> 266 ms (scripts/weight_precision_probe.py; the transposed convs and
+    # the k1 convs are the precision-sensitive ones and keep the (hi, lo) pair)
+    W_SINGLE = r"res_unit.\.conv1"
+
     def __init__(self, sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False,
-                 state_dict=None, precision="fp32", split_min_ch=512, split_res_min_ch=64):
+                 state_dict=None, precision="fp32", split_min_ch=512, split_res_min_ch=64, w_single=None):
         super().__init__(sample_rate, orig_sample_rate, mode)
+        self.w_single = w_single
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
         # activated tensors (MMA operands) / raw residual-stream tensors with >= this many channels travel as (hi, lo) bf16 planes
@@ -133,7 +139,7 @@ class DAC(Codec):
         """Conv1d [Cout,Cin,K] -> [Cout][K*Cin] (column = tap*Cin + c; a stride-s / kernel-2s conv read through the
         s-phase view has exactly this column order)."""
         w = packing.fold_weight_norm(sd, prefix)
-        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"])
+        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"], split=self._w_split(prefix))
         self._tcw.append(W)
         return W
 
@@ -161,7 +167,7 @@ class DAC(Codec):
     def _tcw_convtr(self, sd, prefix, stride):
         w = packing.fold_weight_norm(sd, prefix)     # [Cin, Cout, 2s]
         pk = packing.pack_convtr(w, stride)          # [2, Cin, s*Cout]
-        W = TcWeights(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride))
+        W = TcWeights(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride), split=self._w_split(prefix))
         self._tcw.append(W)
         return W
 

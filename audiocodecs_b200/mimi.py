@@ -27,8 +27,14 @@ class Mimi(Codec):
     def _hop(self):
         return 1920
 
-    def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32"):
+    # single-plane weights on the decoder side only (codes are untouched): decoder transformer GEMMs and the decoder's residual
+    # blocks; decoder SI-SNR 51.8 -> 49.2 dB, step 61.6 -> 58.7 ms at 128 clips (scripts/weight_precision_probe.py)
+    W_SINGLE = r"^decoder_transformer|^decoder\.layers.*block"
+
+    def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32",
+                 w_single=None):
         super().__init__(sample_rate, 24000, mode)
+        self.w_single = w_single
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
         self.num_codebooks = num_codebooks
@@ -137,18 +143,18 @@ class Mimi(Codec):
         return self._specs + self._tcw
 
     # ------------------------------------------------------------------ bf16 tensor path: packing
-    def _tw(self, w, bias=None):
-        W = TcWeights(w, bias)
+    def _tw(self, w, bias=None, name=""):
+        W = TcWeights(w, bias, split=self._w_split(name))
         self._tcw.append(W)
         return W
 
     def _tw_conv(self, sd, prefix):
         w = packing.fold_weight_norm(sd, prefix)  # [Cout, Cin, K] -> [Cout][K*Cin], column = tap*Cin + c
-        return self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"])
+        return self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"], prefix)
 
     def _tw_convtr(self, sd, prefix, stride):
         pk = packing.pack_convtr(packing.fold_weight_norm(sd, prefix), stride)  # [2, Cin, s*Cout]
-        return self._tw(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride))
+        return self._tw(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride), prefix)
 
     def _tw_transformer(self, sd, name):
         out = []
@@ -157,7 +163,8 @@ class Mimi(Codec):
             qkv = torch.cat([sd[p + f"self_attn.{w}.weight"].float() for w in ("q_proj", "k_proj", "v_proj")], dim=0)
             o = sd[p + "self_attn.o_proj.weight"].float() * sd[p + "self_attn_layer_scale.scale"].float().view(-1, 1)
             fc2 = sd[p + "mlp.fc2.weight"].float() * sd[p + "mlp_layer_scale.scale"].float().view(-1, 1)
-            out.append((self._tw(qkv), self._tw(o), self._tw(sd[p + "mlp.fc1.weight"].float()), self._tw(fc2)))
+            out.append((self._tw(qkv, None, p + "qkv"), self._tw(o, None, p + "o"), self._tw(sd[p + "mlp.fc1.weight"].float(), None, p + "fc1"),
+                        self._tw(fc2, None, p + "fc2")))
         return out
 
     def _build_tc(self, sd):
@@ -170,7 +177,7 @@ class Mimi(Codec):
             self._tenc_last = self._tw_conv(sd, f"encoder.layers.{idx + 1}.conv")
             self._tenc_tr = self._tw_transformer(sd, "encoder_transformer")
             w = packing.fold_weight_norm(sd, "downsample.conv")  # [512, 512, 4], no bias
-            self._tdown = self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd.get("downsample.conv.bias"))
+            self._tdown = self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd.get("downsample.conv.bias"), "downsample.conv")
         if self.mode != "encode":
             self._tdec_tr = self._tw_transformer(sd, "decoder_transformer")
             self._tdec_first = self._tw_conv(sd, "decoder.layers.0.conv")

@@ -18,7 +18,11 @@ else:
 B = int(sys.argv[3]) if len(sys.argv) > 3 else B
 codec = codec.eval().to(dev)
 sig = (torch.randn(B, sr * 10, generator=torch.Generator().manual_seed(999)) * 0.1).to(dev)
-for _ in range(steps):
+for i in range(steps):
+    if i == steps - 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # with `ncu --profile-from-start off` only the last (tuned) step is captured
     rec = codec.toks_to_sig(codec.sig_to_toks(sig))
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done", tuple(rec.shape))
