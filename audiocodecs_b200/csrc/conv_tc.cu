@@ -146,14 +146,6 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
             if (any_res && item + EPI_WARPS / 4 < items) fetch_res(b, mg, nt, g, c);
             tmem_ld_wait();
             if (!ok) continue;
-            if (p.epi >= AC_EPI_COL0) {
-                // single-output-channel layer (Cout = 1 padded to a 16-column tile): one fp32 sample per row, coalesced across lanes
-                if (n0 == 0) {
-                    const float s = __uint_as_float(v[0]) + bias_s[0];
-                    p.y32[(long long)b * p.y32_bs + m] = p.epi == AC_EPI_COL0_TANH ? tanhf(s) : s;
-                }
-                continue;
-            }
             if (wide && flat >= 0 && flat + 16 <= p.out_valid && n0 + 16 <= p.n_total) {
                 // fast path: the lane's 16 columns are one aligned 32-byte (bf16) / 64-byte (fp32) run per output plane
                 float o[16];
@@ -170,6 +162,9 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                 if (p.epi == AC_EPI_GELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) o[i] = ac::gelu_erf(o[i]);
+                } else if (p.epi == AC_EPI_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = tanhf(o[i]);
                 }
                 if (has_res) {
                     add_bf16x16(o, rcur[0], rcur[1]);
@@ -234,6 +229,9 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                 if (p.epi == AC_EPI_GELU) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = ac::gelu_erf(o[i]);
+                } else if (p.epi == AC_EPI_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = tanhf(o[i]);
                 }
                 if (has_res) {
                     add_bf16x8(o, p.res + (long long)b * p.res_bs + f);
@@ -516,7 +514,6 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     AC_REQUIRE(d->batch > 0 && d->m_rows > 0 && d->n_total >= 16 && d->n_total % 8 == 0 && d->n_total <= 8192,
                "ac_conv_tc: bad sizes (batch %d rows %d n %d)", d->batch, d->m_rows, d->n_total);
     AC_REQUIRE(d->y || d->y_act || d->y32, "ac_conv_tc: no output");
-    AC_REQUIRE(d->epi < AC_EPI_COL0 || (d->y32 && !d->y && !d->y_act && d->n_total == 16), "ac_conv_tc: COL0 epilogue needs y32 only and n_total 16");
     AC_REQUIRE(d->out_shift % 8 == 0 && d->out_valid % 8 == 0, "ac_conv_tc: out_shift/out_valid must be multiples of 8");
     AC_REQUIRE(d->act != AC_ACT_SNAKE || (d->alpha && d->act_mod > 0 && d->act_mod % 8 == 0 && ((uintptr_t)d->alpha & 15) == 0),
                "ac_conv_tc: snake needs a 16-byte aligned alpha and act_mod % 8 == 0");

@@ -195,7 +195,7 @@ class DAC(Codec):
                 p = f"decoder.block.{i}"
                 self._tdec.append((self._alpha(sd, p + ".snake1"), self._tcw_convtr(sd, p + ".conv_t1", s), s, self._tc_units(sd, p)))
             self._tdec_last_alpha = self._alpha(sd, "decoder.snake1")
-            self._tdec_last = tc.last_conv_weights(self._dec[-1])  # Cout = 1: row 0 of a 16-row tile (COL0 epilogue)
+            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1])  # Cout = 1 as a stride-16 conv with 16 outputs
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
@@ -288,10 +288,12 @@ class DAC(Codec):
             tc.conv_tc(Wtr, [Src(xs, taps=2, shift=-1)], L + 1, y=x, y_act=us, act=ACT_SNAKE, alpha=units[0][0].t, act_mod=C,
                        out_rows=Lout, out_ch=C, out_shift=p * C, name="convtr_tc")
             nxt = self._tdec[bi + 1][0] if bi + 1 < len(self._tdec) else self._tdec_last_alpha
-            xs = self._tc_run_units(units, x, us, nxt)
+            # the last layer (k7, zero padding 3) reads 16-sample view rows: 3 zero rows in front, 13 behind
+            xs = self._tc_run_units(units, x, us, nxt, out_halo=(3, 13) if bi + 1 == len(self._tdec) else (0, 0))
             L = Lout
-        # last layer (Cout = 1, k7, zero padding 3, tanh) on the tap-GEMM kernel: column 0 of a 16-column tile
-        return tc.conv_last_tc(self._tdec_last, xs, 7, shift=-3, tanh=True)
+        # last layer (Cout = 1, k7, zero padding 3, tanh) on the tap-GEMM kernel, 16 samples per GEMM row
+        xs.fill_halo(PAD_ZERO)
+        return tc.conv_last_phased(self._tdec_last, xs, tanh=True)
 
     # ------------------------------------------------------------------ pieces
     def _stack(self, layers, x):

@@ -192,7 +192,7 @@ class Encodec(Codec):
             for r in RATIOS:
                 self._tdec.append((self._tc_convtr(sd, f"decoder.layers.{idx}", r), self._tc_resblock(sd, f"decoder.layers.{idx + 1}"), r))
                 idx += 3
-            self._tdec_last = tc.last_conv_weights(self._dec_last)  # Cout = 1: row 0 of a 16-row tile (COL0 epilogue)
+            self._tdec_last = tc.last_conv_weights_phased(self._dec_last)  # Cout = 1 as a stride-16 conv with 16 outputs
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor-path execution
@@ -293,12 +293,14 @@ class Encodec(Codec):
             # transposed conv: 2-tap GEMM over n = (phase, cout); row -1 reads as zero (TMA OOB fill)
             tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C,
                        name="convtr_tc")
-            ye = Act(B, Lout, C, dev, hl=6 if i == len(self._tdec) - 1 else 0, split=sp)
+            last = i == len(self._tdec) - 1
+            ye = Act(B, Lout, C, dev, hl=6 if last else 0, hr=10 if last else 0, split=sp)
             self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
             L = Lout
-        # last layer (Cout = 1, k7, causal reflect padding in the halo rows) on the tap-GEMM kernel: column 0 of a 16-column tile
+        # last layer (Cout = 1, k7, causal reflect padding in the 6 left halo rows) on the tap-GEMM kernel, 16 samples per
+        # GEMM row; the 10 right halo rows only pad the buffer to whole 16-sample view rows (they meet zero weights)
         ye.fill_halo(PAD_REFLECT, 7 if L <= 6 else 0)
-        return tc.conv_last_tc(self._tdec_last, ye, 7, origin=-6, rows=L + 6)
+        return tc.conv_last_phased(self._tdec_last, ye)
 
     # ------------------------------------------------------------------ pieces
     def _num_quantizers(self):

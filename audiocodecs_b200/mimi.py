@@ -186,7 +186,7 @@ class Mimi(Codec):
                 self._tdec.append((self._tw_convtr(sd, f"decoder.layers.{idx}.conv", r), self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.1.conv"),
                                    self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.3.conv"), r))
                 idx += 3
-            self._tdec_last = tc.last_conv_weights(self._dec[-1])  # Cout = 1: row 0 of a 16-row tile (COL0 epilogue)
+            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1])  # Cout = 1 as a stride-16 conv with 16 outputs
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
@@ -270,17 +270,20 @@ class Mimi(Codec):
         ye = Act(B, N, C, dev, split=True)
         tc.conv_tc(self._tdec_first, [Src(za, taps=7, shift=-6)], N, y_act=ye, act=ACT_ELU, name="conv_k7_tc")
         L = N
-        for Wtr, Wk3, Wk1, r in self._tdec:
+        for i, (Wtr, Wk3, Wk1, r) in enumerate(self._tdec):
             C = C // 2
             Lout = L * r
             sp = C >= SPLIT_MIN_CH
             x = Act(B, Lout, C, dev, split=sp)
             xe = Act(B, Lout, C, dev, split=sp)
             tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C, name="convtr_tc")
-            ye = Act(B, Lout, C, dev, split=sp)
+            last = i == len(self._tdec) - 1   # the last layer reads 16-sample view rows: causal zero halo + pad to whole rows
+            pl = self._dec[-1].taps - 1
+            ye = Act(B, Lout, C, dev, hl=pl if last else 0, hr=(-pl) % 16 if last else 0, split=sp)
             self._tc_resblock(Wk3, Wk1, x, xe, ye)
             L = Lout
-        return tc.conv_last_tc(self._tdec_last, ye, self._dec[-1].taps, shift=-(self._dec[-1].taps - 1))
+        ye.fill_halo(PAD_ZERO)
+        return tc.conv_last_phased(self._tdec_last, ye)
 
     # ------------------------------------------------------------------ pieces
     def _seanet(self, layers, x):

@@ -13,7 +13,7 @@ from ._lib import AcConvF32
 
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 ACT_NONE, ACT_ELU, ACT_SNAKE = 0, 1, 2
-EPI_NONE, EPI_TANH, EPI_GELU, EPI_COL0, EPI_COL0_TANH = 0, 1, 2, 4, 5
+EPI_NONE, EPI_TANH, EPI_GELU = 0, 1, 2
 
 
 class Profiler:

@@ -40,8 +40,6 @@ extern "C" {
 #define AC_EPI_NONE 0
 #define AC_EPI_TANH 1 /* HF/dac:437 */
 #define AC_EPI_GELU 2 /* HF/mimi:852-866 (exact erf GELU) */
-#define AC_EPI_COL0 4      /* ac_conv_tc only: the layer has ONE real output channel (column 0 of a 16-column tile): y32[b][m] = acc[m][0] */
-#define AC_EPI_COL0_TANH 5 /* same, followed by tanh (DAC's last layer, HF/dac:437) */
 
 /*
  * Generic "tap-GEMM" 1-D convolution, fp32 SIMT (the exact-parity path and the shapes the tensor
