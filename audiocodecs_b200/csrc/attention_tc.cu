@@ -257,6 +257,53 @@ attention_tc_kernel(const AttnParams p) {
     }
 }
 
+// LayerNorm over the channel axis with the result written as the split-bf16 activation the next GEMM reads (one warp per
+// row, two-pass mean / variance in fp32 as ac_layernorm_f32; C <= 1024, a multiple of 128).
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                       __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, long long rows, int rows_per_clip, int C,
+                       long long out_bs, float eps) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = C / 128;  // float4 per lane
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < nv) { v[k] = __ldg(xr + lane + 32 * k); s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < nv) {
+            const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+    const long long off = (row / rows_per_clip) * out_bs + (row % rows_per_clip) * C;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < nv) {
+            const int c = 4 * (lane + 32 * k);
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+            const float y0 = (v[k].x - mean) * rstd * ww.x + bb.x, y1 = (v[k].y - mean) * rstd * ww.y + bb.y;
+            const float y2 = (v[k].z - mean) * rstd * ww.z + bb.z, y3 = (v[k].w - mean) * rstd * ww.w + bb.w;
+            const uint32_t h0 = tcc::pack_bf16(y0, y1), h1 = tcc::pack_bf16(y2, y3);
+            *reinterpret_cast<uint2*>(o_hi + off + c) = make_uint2(h0, h1);
+            if (o_lo) {
+                const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&h0), a1 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
+                *reinterpret_cast<uint2*>(o_lo + off + c) = make_uint2(tcc::pack_bf16(y0 - __low2float(a0), y1 - __high2float(a0)),
+                                                                       tcc::pack_bf16(y2 - __low2float(a1), y3 - __high2float(a1)));
+            }
+        }
+}
+
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ table, int T, int half) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= T * half) return;
@@ -268,6 +315,16 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __r
 }
 
 }  // namespace
+
+extern "C" int ac_layernorm_split_bf16(const float* x, const float* w, const float* b, void* out_hi, void* out_lo, int32_t batch,
+                                       int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, void* stream) {
+    AC_REQUIRE(x && w && b && out_hi && batch > 0 && rows_per_clip > 0, "ac_layernorm_split_bf16: bad arguments");
+    AC_REQUIRE(C > 0 && C <= 1024 && C % 128 == 0 && out_bstride % 4 == 0, "ac_layernorm_split_bf16: C %d (multiple of 128, <= 1024)", C);
+    const long long rows = (long long)batch * rows_per_clip;
+    layernorm_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        x, w, b, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, rows, rows_per_clip, C, out_bstride, eps);
+    return ac::finish_launch("ac_layernorm_split_bf16");
+}
 
 extern "C" int ac_rope_table_f32(const float* inv_freq, float* table, int32_t T, int32_t half, void* stream) {
     AC_REQUIRE(inv_freq && table && T > 0 && half > 0, "ac_rope_table_f32: bad arguments");

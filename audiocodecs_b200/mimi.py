@@ -168,6 +168,8 @@ class Mimi(Codec):
         return out
 
     def _build_tc(self, sd):
+        q = "quantizer.{}_residual_vector_quantizer.{}"
+        proj = lambda which, name: packing.fold_weight_norm(sd, q.format(which, name))[:, :, 0]   # 1x1 conv, no bias: [out, in]
         if self.mode != "decode":
             idx, self._tenc = 1, []
             for r in reversed(RATIOS):
@@ -176,10 +178,16 @@ class Mimi(Codec):
                 idx += 3
             self._tenc_last = self._tw_conv(sd, f"encoder.layers.{idx + 1}.conv")
             self._tenc_tr = self._tw_transformer(sd, "encoder_transformer")
+            self._tsem_in = self._tw(proj("semantic", "input_proj"), None, "quantizer.semantic.input_proj")
+            self._tac_in = self._tw(proj("acoustic", "input_proj"), None, "quantizer.acoustic.input_proj")
             w = packing.fold_weight_norm(sd, "downsample.conv")  # [512, 512, 4], no bias
             self._tdown = self._tw(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd.get("downsample.conv.bias"), "downsample.conv")
         if self.mode != "encode":
             self._tdec_tr = self._tw_transformer(sd, "decoder_transformer")
+            # output_proj of the semantic and the acoustic sum as ONE GEMM over the two gathered sources (K = 256 + 256)
+            self._tsem_out = self._tw(proj("semantic", "output_proj"), None, "quantizer.semantic.output_proj")
+            self._tq_out = self._tw(torch.cat([proj("semantic", "output_proj"), proj("acoustic", "output_proj")], dim=1), None,
+                                    "quantizer.output_proj")
             self._tdec_first = self._tw_conv(sd, "decoder.layers.0.conv")
             idx, self._tdec = 2, []
             for r in RATIOS:
@@ -222,11 +230,11 @@ class Mimi(Codec):
         qkv = torch.empty((B, T, 3 * C), device=dev, dtype=torch.float32)
         rope = self._rope_table(T, dev)
         for (ln, *_), (Wqkv, Wo, Wfc1, Wfc2) in zip(layers, tws):
-            ops.f32_to_act(ops.layernorm(h, getattr(self, ln[0]), getattr(self, ln[1])), xa)
+            ops.layernorm_act(h, getattr(self, ln[0]), getattr(self, ln[1]), xa)
             tc.conv_tc(Wqkv, [Src(xa)], T, y32=qkv, name="tr_qkv_tc")
             ops.attention_tc(qkv, rope, HEADS, HEAD_DIM, WINDOW, out_act=xa)
             tc.conv_tc(Wo, [Src(xa)], T, res32=h, y32=h, name="tr_o_tc")
-            ops.f32_to_act(ops.layernorm(h, getattr(self, ln[2]), getattr(self, ln[3])), xa)
+            ops.layernorm_act(h, getattr(self, ln[2]), getattr(self, ln[3]), xa)
             tc.conv_tc(Wfc1, [Src(xa)], T, y=fa, epi=EPI_GELU, name="tr_fc1_tc")
             tc.conv_tc(Wfc2, [Src(fa)], T, res32=h, y32=h, name="tr_fc2_tc")
         return h
@@ -305,7 +313,7 @@ class Mimi(Codec):
             h = ops.conv(fc2, ops.conv(fc1, x), res=h)
         return h
 
-    def _embeddings(self, sig):
+    def _embeddings(self, sig, want_act=False):
         """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
         if self.precision == "bf16":
             h = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
@@ -317,8 +325,9 @@ class Mimi(Codec):
             ops.f32_to_act(h, ha)
             ha.fill_halo(PAD_REPLICATE)
             emb = torch.empty((B, N, C), device=h.device, dtype=torch.float32)
-            tc.conv_tc(self._tdown, [Src(ha, taps=2, origin=-2, phases=2, rows=N + 1)], N, y32=emb, name="downsample_tc")
-            return emb
+            ea = Act(B, N, C, h.device, split=True) if want_act else None   # split-bf16 copy for the quantizer's input_proj GEMMs
+            tc.conv_tc(self._tdown, [Src(ha, taps=2, origin=-2, phases=2, rows=N + 1)], N, y32=emb, y=ea, name="downsample_tc")
+            return (emb, ea) if want_act else emb
         else:
             x = self._seanet(self._enc, sig.contiguous()[:, :, None])
             x = self._run_transformer(self._enc_tr, x)
@@ -345,11 +354,21 @@ class Mimi(Codec):
     def _sig_to_toks(self, sig, length):
         K = self.num_codebooks
         self._check_k(K)
-        emb = self._embeddings(sig)
-        B, N, _ = emb.shape
-        toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
-        xs = ops.conv(self._semantic_in, emb)
-        xa = ops.conv(self._acoustic_in, emb) if K > 1 else None
+        if self.precision == "bf16":
+            emb, ea = self._embeddings(sig, want_act=True)
+            B, N, _ = emb.shape
+            toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
+            xs = torch.empty((B, N, self._tsem_in.n_total), device=sig.device, dtype=torch.float32)
+            tc.conv_tc(self._tsem_in, [Src(ea)], N, y32=xs, name="rvq_in_proj_tc")
+            if K > 1:
+                xa = torch.empty_like(xs)
+                tc.conv_tc(self._tac_in, [Src(ea)], N, y32=xa, name="rvq_in_proj_tc")
+        else:
+            emb = self._embeddings(sig)
+            B, N, _ = emb.shape
+            toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
+            xs = ops.conv(self._semantic_in, emb)
+            xa = ops.conv(self._acoustic_in, emb) if K > 1 else None
         if self.precision == "bf16":  # tcgen05 distance GEMM + exact fp32 re-score (same decisions as the fp32 kernel)
             ops.rvq_encode_tc(xs.view(B * N, -1), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, K), 1, code_offset=0,
                               stage0=0, metric=1)
@@ -379,7 +398,23 @@ class Mimi(Codec):
         return out
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/mimi.py:144-148 ; HF/mimi:1613-1631
-        z = self._toks_to_qfeats(toks, length)
+        if self.precision == "bf16":  # gather-sums straight into split-bf16 operands, both output_proj as one GEMM
+            B, N, K = toks.shape
+            self._check_k(K)
+            toks = toks.to(torch.int64).contiguous()
+            dev = toks.device
+            D = self.codebooks.shape[2]
+            sa = Act(B, N, D, dev, split=True)
+            ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks[:1], 1, sa, code_offset=0, err_flag=self._err)
+            z = torch.empty((B, N, self._tq_out.n_total), device=dev, dtype=torch.float32)
+            if K > 1:
+                aa = Act(B, N, D, dev, split=True)
+                ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks[1:], K - 1, aa, code_offset=1, err_flag=self._err)
+                tc.conv_tc(self._tq_out, [Src(sa), Src(aa)], N, y32=z, name="rvq_out_proj_tc")
+            else:
+                tc.conv_tc(self._tsem_out, [Src(sa)], N, y32=z, name="rvq_out_proj_tc")
+        else:
+            z = self._toks_to_qfeats(toks, length)
         z = ops.upsample_dw(z, self.up_w)
         if self.precision == "bf16":
             return self._decoder_tc(self._tc_transformer(self._dec_tr, self._tdec_tr, z))

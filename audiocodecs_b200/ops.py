@@ -383,6 +383,18 @@ def attention(qkv, inv_freq, heads, head_dim, window):
     return out
 
 
+def layernorm_act(x, w, b, out, eps=1e-5):
+    """x [B, L, C] fp32 contiguous -> LayerNorm over C written into the tc.Act `out` (hi [+lo] planes)."""
+    _need_cuda(x, w, b)
+    assert x.is_contiguous() and x.dtype == torch.float32 and tuple(x.shape) == (out.B, out.L, out.C)
+    vp = lambda v: ctypes.c_void_p(v) if v is not None else None
+    t0 = _PROFILER.begin() if _PROFILER else None
+    _lib.check(_lib.lib().ac_layernorm_split_bf16(_ptr(x), _ptr(w), _ptr(b), vp(out.row_ptr(0)), vp(out.lo_ptr(0)), out.B, out.L, out.C,
+                                                  out.bstride, eps, _stream()), "ac_layernorm_split_bf16")
+    if _PROFILER:
+        _PROFILER.end("layernorm_split_kernel", t0, 0.0, 8.0 * x.numel())
+
+
 def rope_table(inv_freq, T):
     """[T, 2*len(inv_freq)] fp32: cos | sin of position * inv_freq (HF/mimi:515-558)."""
     _need_cuda(inv_freq)

@@ -316,6 +316,9 @@ AC_API int ac_upsample_dw_f32(const float* x, const float* w, float* y, int32_t 
  * HF/mimi:515-558).  Output: fp32 [B][T][H*D] (out32) and/or split-bf16 planes out_hi [+ out_lo] with batch stride
  * out_bstride (elements) -- the activation layout the output-projection GEMM reads.  No window limit.
  */
+/* LayerNorm (as ac_layernorm_f32) written straight into split-bf16 planes [B] x out_bstride + [rows_per_clip][C]. */
+AC_API int ac_layernorm_split_bf16(const float* x, const float* w, const float* b, void* out_hi, void* out_lo, int32_t batch,
+                                   int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, void* stream);
 AC_API int ac_rope_table_f32(const float* inv_freq, float* table, int32_t T, int32_t half, void* stream);
 AC_API int ac_attention_tc(const float* qkv, const float* rope, float* out32, void* out_hi, void* out_lo, int64_t out_bstride,
                            int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, void* stream);
