@@ -7,6 +7,7 @@ from .dac import DAC
 from .encodec import Encodec
 from .mimi import Mimi
 from . import shard  # noqa: F401  (clip sharding across GPUs)
+from .graphs import GraphedCodec
 
 __version__ = "0.1.0"
-__all__ = ["Codec", "Encodec", "DAC", "Mimi"]
+__all__ = ["Codec", "Encodec", "DAC", "Mimi", "GraphedCodec"]

@@ -34,3 +34,16 @@ for name, codec in codecs.items():
     print(json.dumps({"codec": name, "audio_s": secs, "batch": 1, "sample_rate": 16000, "t_enc_ms": round(t_enc * 1e3, 3),
                       "t_dec_ms": round(t_dec * 1e3, 3), "rtf": round((t_enc + t_dec) / secs, 6), "inverse_rtf": round(secs / (t_enc + t_dec), 1),
                       "toks": list(toks.shape), "rec": list(rec.shape)}), flush=True)
+    # the same two calls replayed as CUDA graphs (audiocodecs_b200.GraphedCodec): one driver call per direction
+    g = A.GraphedCodec(codec, sig)
+    same = bool((g.sig_to_toks(sig) == toks).all()) and bool((g.toks_to_sig(toks) == rec).all())
+    torch.cuda.synchronize()
+    t_enc = t_dec = 0.0
+    for _ in range(reps):
+        ev[0].record(); gt = g.sig_to_toks(sig); ev[1].record(); g.toks_to_sig(gt); ev[2].record()
+        torch.cuda.synchronize()
+        t_enc += ev[0].elapsed_time(ev[1]); t_dec += ev[1].elapsed_time(ev[2])
+    t_enc, t_dec = t_enc / reps / 1e3, t_dec / reps / 1e3
+    print(json.dumps({"codec": name, "cuda_graphs": True, "identical_to_eager": same, "t_enc_ms": round(t_enc * 1e3, 3),
+                      "t_dec_ms": round(t_dec * 1e3, 3), "rtf": round((t_enc + t_dec) / secs, 6),
+                      "inverse_rtf": round(secs / (t_enc + t_dec), 1)}), flush=True)

@@ -112,3 +112,21 @@ def test_host_pipeline_matches_direct_calls(encodec_sd, dev):
     for (out, ev), ref in zip(results, direct):
         ev.synchronize()
         assert torch.equal(out, ref)
+
+
+def test_cuda_graph_replay_matches_eager(encodec_sd, dev):
+    """GraphedCodec: the captured tokenize / detokenize graphs give the eager calls' results bit for bit, also on new inputs
+    of the captured shape, and refuse other shapes."""
+    import audiocodecs_b200 as A
+    codec = A.Encodec(24000, 24000, num_codebooks=8, state_dict=encodec_sd).eval().to(dev)
+    sig = make_input(5, 2, 9600).to(dev)
+    g = A.GraphedCodec(codec, sig)
+    for seed in (5, 6, 7):
+        s = make_input(seed, 2, 9600).to(dev)
+        toks = codec.sig_to_toks(s)
+        rec = codec.toks_to_sig(toks)
+        assert torch.equal(g.sig_to_toks(s), toks)
+        assert torch.equal(g.toks_to_sig(toks), rec)
+        assert torch.equal(g.reconstruct(s), rec)
+    with pytest.raises(ValueError):
+        g.sig_to_toks(make_input(1, 1, 9600).to(dev))
