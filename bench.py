@@ -32,8 +32,14 @@ WORKLOADS = {
 
 
 # per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, averaged over every launch of the kernel in one
-# full-size EnCodec step) from the committed ncu launch list profiles/r01c_launches.csv; None when not captured
-NCU_TRAFFIC = {"conv_tc_kernel": 1.097e9, "resunit_tc_kernel": 1.938e9, "lstm_tc_kernel": 4.759e8, "rvq_encode_tc_kernel": 3.28e7}
+# full-size step) from the committed ncu launch lists profiles/r01h_launches.csv (EnCodec), r01h_mimi_launches.csv,
+# r01h_dac_launches.csv; None when not captured
+NCU_TRAFFIC = {
+    "encodec": {"conv_tc_kernel": 1.194e9, "resunit_tc_kernel": 2.909e9, "lstm_tc_kernel": 4.77e8, "rvq_encode_tc_kernel": 3.3e7},
+    "mimi": {"conv_tc_kernel": 8.84e8, "resunit_tc_kernel": 9.416e9, "attention_tc_kernel": 2.38e8},
+    "dac": {"conv_tc_kernel": 8.431e9, "resunit_tc_kernel": 2.2226e10},
+}
+NCU_TRAFFIC["encodec32"] = NCU_TRAFFIC["encodec"]
 
 
 def load_peaks():
@@ -226,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         roofline = {"kernel": name, "bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                     "frac": round(tflops / peaks["tf_sus"], 4)}
-    ncu = NCU_TRAFFIC.get(name) if args.codec in ("encodec", "encodec32") else None
+    ncu = NCU_TRAFFIC.get(args.codec, {}).get(name)
     roofline.update({"traffic": ncu, "peak_source": peaks["src"] + (" (copy bandwidth)" if roofline["bound"] == "hbm" else " (sustained bf16)"),
                      "flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
                      "tensor_tflops": round(tflops, 2), "launches_per_step": d["n"], "ms_per_step": round(d["ms"], 3),
