@@ -34,7 +34,10 @@ struct FirstP {
 };
 
 // block = (C/8) x 32 threads; one block pass = 32 time steps x C channels; a block owns TILE time steps.
-template <int C>
+// The kernel was instruction-issue bound (ncu: 68 % issue slots, 265 instructions per 8 outputs against 1.9 GB of stores):
+// ACT and the tap count are compile-time (KT = 0: run-time taps) and ELU goes through one MUFU.EX2 (abs error ~1e-7, far
+// below the bf16 rounding of the output), which halves the instruction count.
+template <int C, int ACT, int KT>
 __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
     constexpr int G = C / 8;
     constexpr int TILE = 2048;
@@ -46,7 +49,8 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
     const int tl = tid / G;    // time lane 0..31
     const int vlen = p.vlen ? p.vlen[b] : p.T;
     const float* xb = p.x + (long long)b * p.T;
-    for (int i = tid; i < TILE + p.K - 1; i += blockDim.x) {
+    const int K = KT ? KT : p.K;
+    for (int i = tid; i < TILE + K - 1; i += blockDim.x) {
         const int src = pad_index(t0 + i - p.pad_left, p.T, p.pad_mode, p.reflect_len);
         xs[i] = (src >= 0 && src < vlen) ? __ldg(xb + src) : 0.f;
     }
@@ -54,11 +58,11 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
 #pragma unroll
     for (int j = 0; j < MAXK; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) w[j][c] = j < p.K ? __ldg(p.w + j * C + grp * 8 + c) : 0.f;
+        for (int c = 0; c < 8; ++c) w[j][c] = j < K ? __ldg(p.w + j * C + grp * 8 + c) : 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         bias[c] = p.bias ? __ldg(p.bias + grp * 8 + c) : 0.f;
-        al[c] = p.act == AC_ACT_SNAKE ? __ldg(p.alpha + grp * 8 + c) : 0.f;
+        al[c] = ACT == AC_ACT_SNAKE ? __ldg(p.alpha + grp * 8 + c) : 0.f;
     }
     __syncthreads();
     for (int tt = tl; tt < TILE; tt += 32) {
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
         for (int c = 0; c < 8; ++c) acc[c] = bias[c];
 #pragma unroll
         for (int j = 0; j < MAXK; ++j) {
-            if (j < p.K) {
+            if (j < K) {
                 const float xv = xs[tt + j];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = fmaf(xv, w[j][c], acc[c]);
@@ -84,7 +88,8 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
             float a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                a[c] = p.act == AC_ACT_ELU ? ac::elu_fast(acc[c]) : (p.act == AC_ACT_SNAKE ? ac::snake(acc[c], al[c]) : acc[c]);
+                a[c] = ACT == AC_ACT_ELU ? (acc[c] > 0.f ? acc[c] : exp2f(acc[c] * 1.4426950408889634f) - 1.0f)
+                                         : (ACT == AC_ACT_SNAKE ? ac::snake(acc[c], al[c]) : acc[c]);
             *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + off) =
                 make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
         }
@@ -148,12 +153,20 @@ extern "C" int ac_conv_first_bf16(const float* x, const float* w, const float* b
              T, K, pad_left, pad_mode, reflect_len < T ? T : reflect_len, act};
     dim3 grid((T + 2047) / 2048, batch);
     cudaStream_t s = (cudaStream_t)stream;
+#define AC_FIRST(CC)                                                                                     \
+    do {                                                                                                 \
+        if (act == AC_ACT_ELU && K == 7) conv_first_kernel<CC, AC_ACT_ELU, 7><<<grid, CC * 4, 0, s>>>(p); \
+        else if (act == AC_ACT_ELU) conv_first_kernel<CC, AC_ACT_ELU, 0><<<grid, CC * 4, 0, s>>>(p);      \
+        else if (act == AC_ACT_SNAKE) conv_first_kernel<CC, AC_ACT_SNAKE, 0><<<grid, CC * 4, 0, s>>>(p);  \
+        else conv_first_kernel<CC, AC_ACT_NONE, 0><<<grid, CC * 4, 0, s>>>(p);                            \
+    } while (0)
     switch (C) {
-        case 32: conv_first_kernel<32><<<grid, 128, 0, s>>>(p); break;
-        case 64: conv_first_kernel<64><<<grid, 256, 0, s>>>(p); break;
-        case 96: conv_first_kernel<96><<<grid, 384, 0, s>>>(p); break;
+        case 32: AC_FIRST(32); break;
+        case 64: AC_FIRST(64); break;
+        case 96: AC_FIRST(96); break;
         default: ac::set_error("ac_conv_first_bf16: unsupported channel count %d (32/64/96)", C); return -2;
     }
+#undef AC_FIRST
     return ac::finish_launch("ac_conv_first_bf16");
 }
 
