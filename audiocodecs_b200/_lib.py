@@ -101,7 +101,6 @@ def lib():
         L.ac_attention_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp]
         L.ac_upsample_dw_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
         L.ac_layernorm_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, ctypes.c_float, c_vp]
-        L.ac_wave_to_rows16_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_i32, c_i64, c_vp]
         L.ac_rope_table_f32.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp]
         L.ac_attention_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp]
         L.ac_dac_rvq_encode_f32.argtypes = [c_vp] * 8 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]

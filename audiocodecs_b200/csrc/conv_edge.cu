@@ -26,6 +26,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Snake with the hardware sine, as in the tensor-path epilogues (the output is rounded to bf16)
+__device__ __forceinline__ float snake_fast(float x, float a, float ra) {
+    const float s = __sinf(a * x);
+    return fmaf(ra, s * s, x);
+}
+
 struct FirstP {
     const float* x; const float* w; const float* bias; const float* alpha; const int* vlen;
     __nv_bfloat16* y; __nv_bfloat16* y_act;
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
         const int src = pad_index(t0 + i - p.pad_left, p.T, p.pad_mode, p.reflect_len);
         xs[i] = (src >= 0 && src < vlen) ? __ldg(xb + src) : 0.f;
     }
-    float w[MAXK][8], bias[8], al[8];
+    float w[MAXK][8], bias[8], al[8], ral[8];
 #pragma unroll
     for (int j = 0; j < MAXK; ++j)
 #pragma unroll
@@ -63,6 +69,7 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
     for (int c = 0; c < 8; ++c) {
         bias[c] = p.bias ? __ldg(p.bias + grp * 8 + c) : 0.f;
         al[c] = ACT == AC_ACT_SNAKE ? __ldg(p.alpha + grp * 8 + c) : 0.f;
+        ral[c] = 1.0f / (al[c] + 1e-9f);  // HF/dac:85-99
     }
     __syncthreads();
     for (int tt = tl; tt < TILE; tt += 32) {
@@ -89,7 +96,7 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 a[c] = ACT == AC_ACT_ELU ? (acc[c] > 0.f ? acc[c] : exp2f(acc[c] * 1.4426950408889634f) - 1.0f)
-                                         : (ACT == AC_ACT_SNAKE ? ac::snake(acc[c], al[c]) : acc[c]);
+                                         : (ACT == AC_ACT_SNAKE ? snake_fast(acc[c], al[c], ral[c]) : acc[c]);
             *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + off) =
                 make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
         }
@@ -157,6 +164,7 @@ extern "C" int ac_conv_first_bf16(const float* x, const float* w, const float* b
     do {                                                                                                 \
         if (act == AC_ACT_ELU && K == 7) conv_first_kernel<CC, AC_ACT_ELU, 7><<<grid, CC * 4, 0, s>>>(p); \
         else if (act == AC_ACT_ELU) conv_first_kernel<CC, AC_ACT_ELU, 0><<<grid, CC * 4, 0, s>>>(p);      \
+        else if (act == AC_ACT_SNAKE && K == 7) conv_first_kernel<CC, AC_ACT_SNAKE, 7><<<grid, CC * 4, 0, s>>>(p); \
         else if (act == AC_ACT_SNAKE) conv_first_kernel<CC, AC_ACT_SNAKE, 0><<<grid, CC * 4, 0, s>>>(p);  \
         else conv_first_kernel<CC, AC_ACT_NONE, 0><<<grid, CC * 4, 0, s>>>(p);                            \
     } while (0)

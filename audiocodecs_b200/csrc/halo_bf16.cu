@@ -25,25 +25,6 @@ __global__ void pad_halo_bf16_kernel(__nv_bfloat16* data, int rows, int ch, long
     }
 }
 
-// fp32 waveform [B][T] -> split-bf16 planes laid out as 16-sample rows with one padding row in front and zeros behind:
-// flat position f holds sample t = f - 16; t < 0 is the layer's left padding (reflect: x[-t], zero otherwise), samples at or
-// beyond vlen[b] (the reference's padding mask) and beyond T are zero.  This is the A operand of the Cin = 1 first layer
-// run as a tap-GEMM over 16-sample view rows.
-__global__ void wave_to_rows16_kernel(const float* __restrict__ x, const int* __restrict__ vlen, __nv_bfloat16* __restrict__ o_hi,
-                                      __nv_bfloat16* __restrict__ o_lo, int T, long long total, int pad_mode, long long out_bs) {
-    const int b = blockIdx.y;
-    const int valid = vlen ? min(vlen[b], T) : T;
-    const float* xb = x + (long long)b * T;
-    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
-        long long t = f - 16;
-        if (t < 0) t = pad_mode == AC_PAD_REFLECT ? -t : total;  // `total` is past every valid sample: reads as zero
-        const float v = t < valid ? __ldg(xb + t) : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16(v);
-        o_hi[(long long)b * out_bs + f] = h;
-        o_lo[(long long)b * out_bs + f] = __float2bfloat16(v - __bfloat162float(h));
-    }
-}
-
 // out = act(a + b) on split-bf16 tensors (hi [+lo] planes), 8 elements per thread.
 __global__ void add_act_bf16_kernel(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
                                     const __nv_bfloat16* b_lo, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, long long per_clip,
@@ -111,16 +92,6 @@ extern "C" int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, 
     f32_to_split_kernel<<<dim3((unsigned)blocks, batch), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
                                                                                         per_clip, x_bstride, out_bstride);
     return ac::finish_launch("ac_f32_to_split_bf16");
-}
-
-extern "C" int ac_wave_to_rows16_bf16(const float* x, const int32_t* vlen, void* out_hi, void* out_lo, int32_t batch, int32_t T,
-                                      int64_t total, int32_t pad_mode, int64_t out_bstride, void* stream) {
-    AC_REQUIRE(x && out_hi && out_lo && batch > 0 && batch <= 65535 && T > 0 && total >= 16 + (int64_t)T, "ac_wave_to_rows16_bf16: bad arguments");
-    long long blocks = (total + 255) / 256;
-    if (blocks > 2048) blocks = 2048;
-    wave_to_rows16_kernel<<<dim3((unsigned)blocks, batch), 256, 0, (cudaStream_t)stream>>>(x, vlen, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
-                                                                                          T, total, pad_mode, out_bstride);
-    return ac::finish_launch("ac_wave_to_rows16_bf16");
 }
 
 extern "C" int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,

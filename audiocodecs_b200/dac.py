@@ -183,8 +183,6 @@ class DAC(Codec):
 
     def _build_tc(self, sd):
         if self.mode != "decode":
-            self._tenc_first = tc.first_conv_weights_phased(self._enc[0], 3)
-            self._tcw.append(self._tenc_first[0])
             self._tenc = []
             for i, s in enumerate(self._enc_rates):
                 p = f"encoder.block.{i}"
@@ -245,9 +243,7 @@ class DAC(Codec):
         C = self._enc[0].cout
         x = Act(B, T, C, dev, split=False)   # the Cin=1 edge kernel writes single planes
         xs = Act(B, T, C, dev, split=False)
-        # first layer (Cin = 1, k7, zero padding 3) as a tap-GEMM over 16-sample rows of the waveform
-        tc.conv_first_phased(self._tenc_first[0], self._tenc_first[1], sig, pad_mode=PAD_ZERO, y=x, y_act=xs, act=ACT_SNAKE,
-                             alpha=self._tenc[0][0][0][0].t)
+        ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xs, act=ACT_SNAKE, alpha=self._tenc[0][0][0][0].t)
         L = T
         for bi, (units, a_down, Wdown, s) in enumerate(self._tenc):
             p = math.ceil(s / 2)

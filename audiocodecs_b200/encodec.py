@@ -249,8 +249,6 @@ class Encodec(Codec):
         raw = 32 <= RAW_MAX_CH
         x = Act(B, T, 32, dev, hl=2 if raw else 0)
         xe = None if raw else Act(B, T, 32, dev, hl=2)
-        # (the tap-GEMM form of this Cin = 1 layer, tc.conv_first_phased, measured 0.74 ms against 0.72 ms here: both are bound
-        # by writing the raw + activated copies; DAC, whose Snake epilogue is heavier, uses it)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU, vlen=vlen)
         L = T
         for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):

@@ -257,41 +257,6 @@ def autotune(key, variants):
 LAST_PHASES = 16
 
 
-def first_conv_weights_phased(spec, pad_left, split=True):
-    """Cin = 1 first layer (ops.ConvSpec, w [taps][1][cout]) as a tap-GEMM over 16-sample rows of the waveform: GEMM row n
-    produces samples 16n .. 16n+15 x cout channels (n_total = 16*cout, column j*cout + c) from the view rows n-1, n (and
-    n+1 when the layer also pads on the right): W[j*cout + c][tau] = w[tau - 16 - j + pad_left][c]."""
-    taps, _, cout = spec.w.shape
-    P = LAST_PHASES
-    tv = 2 if pad_left == taps - 1 else 3
-    w = torch.zeros((P, cout, tv * P), dtype=torch.float32, device=spec.w.device)
-    for j in range(P):
-        lo = P + j - pad_left
-        w[j, :, lo:lo + taps] = spec.w[:, 0, :].t()
-    bias = spec.bias.reshape(-1).float().repeat(P) if spec.bias is not None else None
-    return TcWeights(w.reshape(P * cout, -1), bias, split=split), tv
-
-
-def conv_first_phased(W: TcWeights, view_taps, sig, *, pad_mode, y: Act = None, y_act: Act = None, act=ops.ACT_NONE, alpha=None, vlen=None,
-                      name="conv_first_tc"):
-    """sig [B, T] fp32 -> raw / activated Acts [B, T, cout]: the waveform is staged once as split bf16 in 16-sample rows
-    (ac_wave_to_rows16_bf16), then one tap-GEMM launch writes both outputs."""
-    ops._need_cuda(sig)
-    P = LAST_PHASES
-    B, T = sig.shape
-    R = -(-T // P)
-    cout = W.n_total // P
-    wave = Act(B, R, P, sig.device, hl=1, hr=1, split=True)
-    sig = sig.contiguous()
-    t0 = ops._PROFILER.begin() if ops._PROFILER else None
-    _lib.check(_lib.lib().ac_wave_to_rows16_bf16(ops._ptr(sig), ops._ptr(vlen), ctypes.c_void_p(wave.row_ptr(-1)), ctypes.c_void_p(wave.lo_ptr(-1)),
-                                                 B, T, (R + 2) * P, pad_mode, wave.bstride, ops._stream()), "ac_wave_to_rows16_bf16")
-    if ops._PROFILER:
-        ops._PROFILER.end("wave_to_rows16", t0, 0.0, 8.0 * B * T)
-    conv_tc(W, [Src(wave, taps=view_taps, origin=-1, rows=R + 2)], R, y=y, y_act=y_act, act=act, alpha=alpha, act_mod=cout, out_rows=T,
-            out_ch=cout, name=name)
-
-
 def last_conv_weights_phased(spec, split=True):
     """Cout = 1 last layer as a stride-16 convolution with 16 output channels: GEMM row n produces the 16 consecutive samples
     16n .. 16n+15 from the two 16-sample view rows n, n+1 of the padded input (a Toeplitz weight matrix

@@ -271,11 +271,6 @@ AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch,
  * clip.  The skip-add + ELU that follows EnCodec's LSTM (HF/encodec:247 `hidden_states + residual`, then the next
  * layer's ELU), kept out of the latency-bound recurrence kernel.
  */
-/* fp32 waveform [B][T] -> split-bf16 planes of `total` samples per clip (batch stride out_bstride): 16 left-padding samples
- * (reflect of the masked waveform, or zeros), the waveform masked to vlen[b] (HF/encodec:599-601), zeros to the end: the A
- * operand of the Cin = 1 first layer (HF/encodec:82-176, HF/dac:442-472, HF/mimi:214-351) run as a tap-GEMM over 16-sample rows. */
-AC_API int ac_wave_to_rows16_bf16(const float* x, const int32_t* vlen, void* out_hi, void* out_lo, int32_t batch, int32_t T,
-                                  int64_t total, int32_t pad_mode, int64_t out_bstride, void* stream);
 AC_API int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
                            int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,
                            int32_t act, void* stream);

@@ -182,39 +182,3 @@ def test_split_precision_near_fp32():
     assert rel < 3e-5, rel
     rel2 = ((y.float().cpu().double() + ylo.float().cpu().double() - ref).norm() / ref.norm()).item()
     assert rel2 < 5e-5, rel2
-
-
-@pytest.mark.parametrize("T,pad_left,pad_mode,taps", [(4000, 6, "reflect", 7), (1037, 6, "zero", 7), (333, 3, "zero", 7), (5, 6, "reflect", 7)])
-def test_conv_first_phased_vs_torch(T, pad_left, pad_mode, taps):
-    """Cin = 1 first layer as a tap-GEMM over 16-sample rows (Toeplitz weights) vs torch fp32: causal reflect / causal zero /
-    'same' zero padding, ragged lengths, a clip shorter than the padding, the per-clip valid-length mask."""
-    from audiocodecs_b200 import ops, tc
-    from audiocodecs_b200.tc import Act
-    dev = torch.device(DEV)
-    g = torch.Generator().manual_seed(T)
-    B, C = 3, 32
-    w = torch.randn(C, 1, taps, generator=g) * 0.3
-    bias = torch.randn(C, generator=g) * 0.1
-    sig = torch.randn(B, T, generator=g)
-    vlen = torch.tensor([T, max(1, T // 2), max(1, T - 3)], dtype=torch.int32)
-    masked = sig * (torch.arange(T)[None] < vlen[:, None])
-    x = masked[:, None]
-    if pad_mode == "reflect":
-        if T <= pad_left:  # HF _pad1d: zero-extend, reflect, trim
-            ext = F.pad(x, (0, pad_left - T + 1))
-            x = F.pad(ext, (pad_left, 0), mode="reflect")[..., : pad_left + T]
-        else:
-            x = F.pad(x, (pad_left, 0), mode="reflect")
-    else:
-        x = F.pad(x, (pad_left, taps - 1 - pad_left))
-    ref = F.conv1d(x, w, bias).permute(0, 2, 1)  # [B, T, C]
-    spec = ops.ConvSpec(w.permute(2, 1, 0).contiguous(), bias, cout=C, geometry="causal" if pad_left == taps - 1 else "same",
-                        padding=pad_left, pad_mode=ops.PAD_REFLECT if pad_mode == "reflect" else ops.PAD_ZERO)
-    W, tv = tc.first_conv_weights_phased(spec, pad_left)
-    W.apply(lambda t: t.to(dev))
-    y, ye = Act(B, T, C, dev), Act(B, T, C, dev)
-    tc.conv_first_phased(W, tv, sig.to(dev), pad_mode=ops.PAD_REFLECT if pad_mode == "reflect" else ops.PAD_ZERO, y=y, y_act=ye,
-                         act=ops.ACT_ELU, vlen=vlen.to(dev))
-    got = y.data().float().cpu()
-    assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()      # bf16 output rounding
-    assert (ye.data().float().cpu() - F.elu(ref)).abs().max().item() <= 2e-2 * ref.abs().max().item()

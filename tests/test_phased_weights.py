@@ -1,6 +1,6 @@
-"""Host logic of the single-channel edge layers run as tap-GEMMs over 16-sample rows (audiocodecs_b200/tc.py:
-last_conv_weights_phased / first_conv_weights_phased): the Toeplitz weight matrices, multiplied in plain torch over the
-same 16-phase views the kernels read, must reproduce F.conv1d.  CPU only (no kernel is launched)."""
+"""Host logic of the Cout = 1 last layers run as tap-GEMMs over 16-sample rows (audiocodecs_b200/tc.py:
+last_conv_weights_phased): the Toeplitz weight matrix, multiplied in plain torch over the same 16-phase view the kernel
+reads, must reproduce F.conv1d.  CPU only (no kernel is launched)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -32,21 +32,3 @@ def test_last_conv_toeplitz_matches_conv1d(C, taps, pad_left, L):
     got = (a @ Wf.t() + W.bias).reshape(2, -1)
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()   # weights are bf16 hi + lo: ~2^-17 relative
-
-
-@pytest.mark.parametrize("C,taps,pad_left,T", [(32, 7, 6, 333), (64, 7, 3, 1000), (64, 7, 6, 16)])
-def test_first_conv_toeplitz_matches_conv1d(C, taps, pad_left, T):
-    g = torch.Generator().manual_seed(T)
-    w = torch.randn(C, 1, taps, generator=g)
-    b = torch.randn(C, generator=g)
-    x = torch.randn(2, T, generator=g)
-    ref = F.conv1d(F.pad(x[:, None], (pad_left, taps - 1 - pad_left)), w, b).permute(0, 2, 1)   # [B, T, C]
-    W, tv = tc.first_conv_weights_phased(_spec(w, b, geometry="causal" if pad_left == taps - 1 else "same", padding=pad_left), pad_left)
-    assert tv == (2 if pad_left == taps - 1 else 3)
-    Wf = W.w[0].float() + W.w[1].float()
-    R = -(-T // P)
-    flat = F.pad(x, (P, (R + 1) * P - T))                                   # one padding row in front (zeros here), zeros behind
-    view = flat.reshape(2, R + 2, P)
-    a = torch.cat([view[:, k:k + R] for k in range(tv)], dim=-1)            # view rows n-1, n (, n+1) relative to the data
-    got = (a @ Wf.t() + W.bias).reshape(2, R * P, C)[:, :T]
-    assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
