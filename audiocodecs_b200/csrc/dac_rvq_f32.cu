@@ -250,7 +250,7 @@ extern "C" int ac_dac_rvq_encode_f32(const float* z, const float* w_in, const fl
                                      void* stream) {
     AC_REQUIRE(z && w_in && b_in && codebooks && w_out && b_out && codes, "ac_dac_rvq_encode_f32: null pointer");
     AC_REQUIRE(hidden == HD && cb_dim == CD, "ac_dac_rvq_encode_f32: built for hidden %d / codebook dim %d", HD, CD);
-    AC_REQUIRE(rows > 0 && stages > 0 && stages <= 16 && n_codes > 0, "ac_dac_rvq_encode_f32: bad sizes");
+    AC_REQUIRE(rows > 0 && stages > 0 && stages <= 32 && n_codes > 0, "ac_dac_rvq_encode_f32: bad sizes");
     const size_t smem = (size_t)(FR * HD + 3 * FR * CD + FR * (THREADS / FR)) * 4 + (size_t)(FR * (THREADS / FR) + FR) * 4;
     static bool set = false;
     if (!set) {
@@ -268,10 +268,13 @@ extern "C" int ac_dac_rvq_decode_f32(const int64_t* codes, const float* codebook
                                      int32_t code_stride, int32_t* err_flag, void* stream) {
     AC_REQUIRE(codes && codebooks && w_out && b_out && out, "ac_dac_rvq_decode_f32: null pointer");
     AC_REQUIRE(hidden == HD && cb_dim == CD, "ac_dac_rvq_decode_f32: built for hidden %d / codebook dim %d", HD, CD);
-    AC_REQUIRE(rows > 0 && stages > 0 && stages <= 16, "ac_dac_rvq_decode_f32: bad sizes");
-    AC_REQUIRE((rows + DR - 1) / DR <= 65535, "ac_dac_rvq_decode_f32: too many rows for one launch");
-    dac_rvq_decode_kernel<<<dim3(HD / 256, (unsigned)((rows + DR - 1) / DR)), 256, (size_t)DR * stages * CD * 4, (cudaStream_t)stream>>>(
-        codes, codebooks, w_out, b_out, out, rows, n_codes, stages, code_stride, err_flag);
+    AC_REQUIRE(rows > 0 && stages > 0 && stages <= 32, "ac_dac_rvq_decode_f32: bad sizes");
+    const int64_t slice = (int64_t)65535 * DR;  // grid.y limit: launch in slices of at most 65535 row blocks
+    for (int64_t r0 = 0; r0 < rows; r0 += slice) {
+        const int64_t n = rows - r0 < slice ? rows - r0 : slice;
+        dac_rvq_decode_kernel<<<dim3(HD / 256, (unsigned)((n + DR - 1) / DR)), 256, (size_t)DR * stages * CD * 4, (cudaStream_t)stream>>>(
+            codes + r0 * code_stride, codebooks, w_out, b_out, out + r0 * HD, n, n_codes, stages, code_stride, err_flag);
+    }
     return ac::finish_launch("ac_dac_rvq_decode_f32");
 }
 
