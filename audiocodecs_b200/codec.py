@@ -91,6 +91,59 @@ class Codec(torch.nn.Module, ABC):
     def toks_to_qfeats(self, toks, length=None):  # R/codec.py:102-108
         return self._toks_to_qfeats(toks, length)
 
+    def feats_to_sig(self, feats, length=None):  # R/codec.py:109-119 (EnCodec / DAC / Mimi define no `_feats_to_sig`)
+        sig = self._feats_to_sig(feats, length)
+        return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
+
+    # ---- token augmentation (R/codec.py:121-180): the step right after the tokenizer in the downstream recipes.  Host-side
+    # torch ops over `embs()` -- sampling is not on the hot path.
+    @torch.no_grad()
+    def logits(self):
+        """[K, C, C]: minus the pairwise Euclidean distance between the code vectors of each codebook, -inf on the diagonal
+        (a code never resamples to itself).  Cached after the first call, returned as a copy (R/codec.py:150-159)."""
+        if getattr(self, "_pair_logits", None) is None:
+            e = self.embs()
+            lg = torch.cdist(e, e).neg_()
+            lg.diagonal(dim1=-2, dim2=-1).fill_(float("-inf"))
+            self._pair_logits = lg
+        return self._pair_logits.clone()
+
+    def resample(self, toks, p=0.2, temp=1.0, top_k=None, top_p=None):
+        """toks [B, N, K] -> a copy in which each token is replaced, with probability p, by a code drawn from
+        softmax(-distance / temp) around it (optionally restricted to the top_k nearest / the top_p nucleus)."""
+        if p <= 0.0:
+            return toks
+        if top_k is not None and top_p is not None:
+            raise NotImplementedError
+        out = toks.clone()
+        K = out.shape[-1]
+        lg = self.logits().to(out.device)                                   # [K, C, C]
+        per_book = out.reshape(-1, K).t()                                   # [K, B*N]
+        rows = lg.gather(1, per_book[..., None].expand(-1, -1, lg.shape[-1]))  # [K, B*N, C]: the row of each current code
+        probs = (rows.reshape(-1, lg.shape[-1]) / temp).softmax(dim=-1)     # [K*B*N, C]
+        if top_k is not None:
+            draw = self._sample_top_k(probs, top_k)
+        elif top_p is not None:
+            draw = self._sample_top_p(probs, top_p)
+        else:
+            draw = probs.multinomial(num_samples=1)[:, 0]
+        draw = draw.reshape(K, -1).t().reshape(out.shape)
+        replace = (torch.rand(out.shape) < p).to(out.device)                # drawn on the CPU generator, as the reference does
+        out[replace] = draw[replace]
+        return out
+
+    def _sample_top_k(self, probs, k):  # R/codec.py:161-168
+        top, idx = probs.topk(k, dim=-1)
+        pick = (top / top.sum(dim=-1, keepdim=True)).multinomial(num_samples=1)
+        return idx.gather(-1, pick)[:, 0]
+
+    def _sample_top_p(self, probs, p):  # R/codec.py:170-180: keep the smallest prefix of the sorted codes whose mass exceeds p
+        srt, idx = probs.sort(dim=-1, descending=True)
+        before = srt.cumsum(dim=-1) - srt
+        srt = srt.masked_fill(before > p, 0.0)
+        pick = (srt / srt.sum(dim=-1, keepdim=True)).multinomial(num_samples=1)
+        return idx.gather(-1, pick)[:, 0]
+
     @abstractmethod
     def embs(self):
         raise NotImplementedError
@@ -112,6 +165,9 @@ class Codec(torch.nn.Module, ABC):
         raise NotImplementedError
 
     def _toks_to_qfeats(self, toks, length):
+        raise NotImplementedError
+
+    def _feats_to_sig(self, feats, length):
         raise NotImplementedError
 
     # ---- plumbing shared by the wrappers
