@@ -261,7 +261,7 @@ def last_conv_weights_phased(spec, split=True):
     """Cout = 1 last layer as a stride-16 convolution with 16 output channels: GEMM row n produces the 16 consecutive samples
     16n .. 16n+15 from the two 16-sample view rows n, n+1 of the padded input (a Toeplitz weight matrix
     W[j][tau*C + c] = w[tau - j][c], 0 <= tau - j < taps).  16 useful accumulator columns per row instead of 1, and
-    ~3.5x fewer (small-N) tcgen05.mma per sample than the column-0 form."""
+    ~3.5x fewer (small-N) tcgen05.mma per sample than a one-output-column GEMM per sample."""
     taps, cin, _ = spec.w.shape
     P = LAST_PHASES
     assert taps <= P + 1
