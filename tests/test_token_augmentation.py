@@ -46,3 +46,21 @@ def test_resample_semantics(codec):
         codec.resample(toks, p=0.5, top_k=2, top_p=0.5)
     with pytest.raises(NotImplementedError):
         codec.feats_to_sig(torch.zeros(1, 2, 128))
+
+
+def test_augmentation_matches_reference_golden(codec):
+    """tests/golden/augment_golden.pt (oracle/make_golden_augment.py: the live reference's `logits()` / `resample()` under
+    fixed torch seeds): same logits, and -- the torch RNG being consumed in the same order -- the same resampled tokens."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "augment_golden.pt"))
+    lg = codec.logits()
+    idx = g["logit_idx"]
+    got = torch.stack([lg[k, idx[:, 0], idx[:, 1]] for k in range(g["K"])])
+    finite = torch.isfinite(g["logit_vals"])
+    assert torch.equal(torch.isfinite(got), finite)
+    assert (got[finite] - g["logit_vals"][finite]).abs().max().item() < 1e-4
+    assert abs(lg[torch.isfinite(lg)].double().sum().item() - g["logit_finite_sum"]) < 1e-6 * abs(g["logit_finite_sum"])
+    for c in g["cases"]:
+        torch.manual_seed(c["seed"])
+        res = codec.resample(g["toks"], p=c["p"], temp=c["temp"], top_k=c["top_k"], top_p=c["top_p"])
+        assert torch.equal(res, c["out"]), c
