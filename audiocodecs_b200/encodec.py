@@ -29,10 +29,11 @@ class Encodec(Codec):
     R/audiocodecs/encodec.py:51) and only its state dict is kept.
     """
 
-    # single-plane weights for the decoder's plain and transposed convolutions (not its residual blocks): decoder SI-SNR
-    # unchanged at 45.1 dB, codes untouched, step 17.8 -> 17.3 ms (scripts/weight_precision_probe.py); the encoder keeps
-    # the (hi, lo) pair everywhere because its error shows up as code flips
-    W_SINGLE = r"^decoder\.layers\.\d+\.conv"
+    # every layer keeps the (hi, lo) weight pair: with single-plane weights everywhere the decoder SI-SNR falls to 39.9 dB
+    # (residual blocks alone: 44.0 dB, their 1x1 tails: 42.3 dB) and encoder-side rounding shows up as code flips
+    # (93.4 -> 90.3 % code match), scripts/weight_precision_probe.py.  Layer names here are `encoder.layers.N`,
+    # `decoder.layers.N`, `....block.1`, `....tail`.
+    W_SINGLE = None
 
     def __init__(self, sample_rate, orig_sample_rate=24000, mode="reconstruct", num_codebooks=8, use_vocos=False,
                  state_dict=None, precision="bf16", w_single=None):
