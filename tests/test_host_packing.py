@@ -103,3 +103,19 @@ def test_projected_dac_rvq_algebra(dac_sd):
     clear = (gaps.permute(0, 2, 1) > 1e-4).long().cumprod(dim=-1).bool()
     assert (got == ref.permute(0, 2, 1))[clear].all()
     assert clear.float().mean().item() > 0.9
+
+
+def test_sub_batch_chunking(encodec_sd):
+    """Codec._chunks: a batch larger than max_chunk_samples is cut into contiguous sub-batches that cover every clip once."""
+    import audiocodecs_b200 as A
+    c = A.Encodec(24000, 24000, state_dict=encodec_sd)
+    c.max_chunk_samples = 10 * 240000
+    assert c._chunks(7, 240000) == [(0, 7)]
+    spans = c._chunks(25, 240000)
+    assert spans == [(0, 10), (10, 20), (20, 25)]
+    assert c._chunks(3, 10 ** 9) == [(0, 1), (1, 2), (2, 3)]          # a clip longer than the budget still runs, alone
+    calls = []
+    out = c._chunked(lambda x, l: calls.append((x.shape[0], None if l is None else tuple(l.tolist()))) or x * 2,
+                     torch.arange(25.0)[:, None], torch.linspace(0.1, 1.0, 25), 240000)
+    assert torch.equal(out, torch.arange(25.0)[:, None] * 2) and [n for n, _ in calls] == [10, 10, 5]
+    assert calls[2][1] == tuple(torch.linspace(0.1, 1.0, 25)[20:].tolist())
