@@ -120,10 +120,15 @@ def lib():
     return _lib
 
 
+class ConfigError(RuntimeError):
+    """an entry point rejected its arguments or found no tiling for the shape (rc = -1); nothing was launched"""
+
+
 def check(rc, what):
     if rc != 0:
         msg = lib().ac_last_error().decode(errors="replace")
-        raise RuntimeError(f"audiocodecs_b200: {what} failed (rc={rc}): {msg}")
+        # rc = -1: argument / configuration check (AC_REQUIRE); rc > 0: a cudaError_t from the launch
+        raise (ConfigError if rc == -1 else RuntimeError)(f"audiocodecs_b200: {what} failed (rc={rc}): {msg}")
 
 
 def launch_count():

@@ -207,12 +207,14 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
 # ---------------------------------------------------------------------------------------------- shape-keyed autotuning
 _TUNED = {}
 TUNE = True  # False: always take the first variant
+TUNE_ERRORS = []  # (key, variant, message) of variants that failed with something other than a configuration error
 
 
 def autotune(key, variants):
     """variants: list of (name, fn) computing the SAME result with different tilings / kernel splits.  The first call for
     a key times every variant on the device (best of 3 after one warm-up run, CUDA events on the current stream) and caches
-    the winner; a variant whose tiling does not fit raises and is skipped.  Later calls dispatch straight to the winner.
+    the winner; a variant whose tiling does not fit (`_lib.ConfigError`, nothing launched) is skipped; a variant that fails to
+    launch is skipped too but recorded in TUNE_ERRORS and named if no variant works.  Later calls dispatch straight to the winner.
     Measured choices replace hand-written heuristics: which tiling wins depends on the layer shape in ways (TMA row
     granularity, weight re-streaming per tile, epilogue / tensor-pipe balance) that the profiles only explained afterwards."""
     name = _TUNED.get(key)
@@ -221,18 +223,22 @@ def autotune(key, variants):
             for vname, fn in variants:  # no tuning: the first variant whose tiling fits
                 try:
                     out = fn()
-                except RuntimeError:
+                except RuntimeError as e:  # _lib.ConfigError: this variant's tiling does not fit the shape (nothing launched)
+                    if not isinstance(e, _lib.ConfigError):
+                        TUNE_ERRORS.append((key, vname, str(e)))  # a launch error: kept for the report below, never silent
                     continue
                 _TUNED[key] = vname
                 return out
-            raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched")
+            raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched {TUNE_ERRORS[-3:]}")
         else:
             saved, ops._PROFILER = ops._PROFILER, None
             times = {}
             for vname, fn in variants:
                 try:
                     fn()
-                except RuntimeError:
+                except RuntimeError as e:  # _lib.ConfigError: this variant's tiling does not fit the shape (nothing launched)
+                    if not isinstance(e, _lib.ConfigError):
+                        TUNE_ERRORS.append((key, vname, str(e)))  # a launch error: kept for the report below, never silent
                     continue
                 best = float("inf")
                 for _ in range(3):
@@ -245,7 +251,7 @@ def autotune(key, variants):
                 times[vname] = best
             ops._PROFILER = saved
             if not times:
-                raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched")
+                raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched {TUNE_ERRORS[-3:]}")
             name = min(times, key=times.get)
         _TUNED[key] = name
     for vname, fn in variants:
