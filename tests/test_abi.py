@@ -42,3 +42,15 @@ def test_constructor_contract(encodec_sd):
     bad = A.Encodec(24000, 24000, num_codebooks=3, state_dict=encodec_sd)
     with pytest.raises(ValueError, match="bandwidth"):
         bad._num_quantizers()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No fallback: with the shared library absent the loader raises and names the build command."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libaudiocodecs_b200.so"))
+    with pytest.raises(RuntimeError, match="not built"):
+        _lib.lib()
+
+
+def test_config_error_is_a_runtime_error():
+    assert issubclass(_lib.ConfigError, RuntimeError)
