@@ -119,3 +119,50 @@ def test_sub_batch_chunking(encodec_sd):
                      torch.arange(25.0)[:, None], torch.linspace(0.1, 1.0, 25), 240000)
     assert torch.equal(out, torch.arange(25.0)[:, None] * 2) and [n for n, _ in calls] == [10, 10, 5]
     assert calls[2][1] == tuple(torch.linspace(0.1, 1.0, 25)[20:].tolist())
+
+
+def test_autotune_skips_and_reports(monkeypatch):
+    """tc.autotune: variants whose tiling does not fit (ConfigError) are skipped silently, launch errors are skipped but
+    recorded, the fastest remaining variant is cached, and the error names the failures when nothing works.  CUDA events are
+    replaced by a fake clock so the selection logic runs on the CPU."""
+    from audiocodecs_b200 import _lib, tc
+
+    clock = {"t": 0.0}
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self):
+            self.t = clock["t"]
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(tc, "_TUNED", {})
+    monkeypatch.setattr(tc, "TUNE_ERRORS", [])
+    calls = []
+
+    def variant(name, cost=None, exc=None):
+        def fn():
+            calls.append(name)
+            if exc is not None:
+                raise exc
+            clock["t"] += cost
+            return name
+        return name, fn
+
+    vs = [variant("nofit", exc=_lib.ConfigError("no tiling fits")), variant("slow", 5.0), variant("broken", exc=RuntimeError("launch failed")),
+          variant("fast", 1.0)]
+    assert tc.autotune(("k", 1), vs) == "fast" and tc._TUNED[("k", 1)] == "fast"
+    assert [e[1] for e in tc.TUNE_ERRORS] == ["broken"]
+    calls.clear()
+    assert tc.autotune(("k", 1), vs) == "fast" and calls == ["fast"]            # cached: straight to the winner
+    monkeypatch.setattr(tc, "TUNE", False)
+    assert tc.autotune(("k", 2), vs) == "slow"                                   # no tuning: the first variant that launches
+    with pytest.raises(RuntimeError, match="no variant"):
+        tc.autotune(("k", 3), vs[:1] + vs[2:3])
