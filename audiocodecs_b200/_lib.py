@@ -65,7 +65,7 @@ class AcLstmTcDesc(ctypes.Structure):
     """mirror of `struct ac_lstm_tc_desc`"""
     _fields_ = [("pre", c_vp), ("w_hh_bf16", c_vp), ("out_hi", c_vp), ("out_lo", c_vp), ("skip_hi", c_vp), ("skip_lo", c_vp),
                 ("final_hi", c_vp), ("final_lo", c_vp), ("skip_bstride", c_i64), ("final_bstride", c_i64),
-                ("final_act", c_i32), ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("dbg", c_vp)]
+                ("final_act", c_i32), ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("dbg", c_vp), ("operand_fp16", c_i32)]
 
 
 def declared_symbols():
@@ -106,8 +106,8 @@ def lib():
         L.ac_dac_rvq_encode_f32.argtypes = [c_vp] * 8 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_dac_rvq_encode_proj_f32.argtypes = [c_vp, c_i32] + [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_dac_rvq_decode_f32.argtypes = [c_vp] * 5 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
-        L.ac_conv_first_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
-                                         c_i32, c_i32, c_i32, c_vp]
+        L.ac_conv_first_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32,
+                                         c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_conv_last_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_lstm_tc.argtypes = [ctypes.POINTER(AcLstmTcDesc), c_vp]
         L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]

@@ -20,6 +20,10 @@ class Codec(torch.nn.Module, ABC):
     # codec rate) is processed in sub-batches so that any batch size fits the 180 GB of a B200 (the clips are
     # independent, so chunking changes nothing but peak memory).  Sub-classes set it from their per-sample footprint.
     max_chunk_samples = 256 * 240000
+    # toks_to_sig / toks_to_qfeats check the token range on entry and raise IndexError like the reference's embedding lookup
+    # (one tiny device reduction + a host sync per call; skipped while a CUDA graph is being captured).  Set to False to
+    # drop the sync: out-of-range tokens then decode as code 0 and only set the kernels' error flag (`codec._err`).
+    strict_tokens = True
 
     def __init__(self, sample_rate, orig_sample_rate, mode="reconstruct"):
         super().__init__()
@@ -37,6 +41,27 @@ class Codec(torch.nn.Module, ABC):
             return self.toks_to_sig(input, length)
         toks = self.sig_to_toks(input, length)
         return self.toks_to_sig(toks, length)
+
+    def _on(self, t):
+        """device guard: every launch of a call goes to the device (and its current stream) that holds the input -- the C-ABI
+        takes raw pointers and a stream, it has no device of its own.  The packed weights must live on the same device."""
+        if not t.is_cuda:
+            raise RuntimeError("audiocodecs_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback. "
+                               "Move the codec and its inputs with .to('cuda').")
+        own = next(self.buffers()).device
+        if own != t.device:
+            raise RuntimeError(f"input on {t.device} but the codec's weights are on {own}: move one of them with .to()")
+        return torch.cuda.device(t.device)
+
+    def _check_toks(self, toks):
+        if not self.strict_tokens or torch.cuda.is_current_stream_capturing():
+            return
+        if toks.dtype.is_floating_point or toks.dtype == torch.bool:
+            raise TypeError(f"tokens must be an integer tensor, got {toks.dtype}")
+        lo, hi = torch.aminmax(toks)
+        lo, hi = int(lo), int(hi)
+        if lo < 0 or hi >= self.vocab_size:
+            raise IndexError(f"token values must lie in [0, {self.vocab_size}), got [{lo}, {hi}]")
 
     def _prep_sig(self, sig, length):
         sig = ops.resample(sig.float(), self.sample_rate, self.orig_sample_rate)
@@ -65,23 +90,28 @@ class Codec(torch.nn.Module, ABC):
 
     @torch.no_grad()
     def sig_to_toks(self, sig, length=None):  # R/codec.py:57-66
-        sig, length = self._prep_sig(sig, length)
-        return self._chunked(self._sig_to_toks, sig, length, sig.shape[-1])
+        with self._on(sig):
+            sig, length = self._prep_sig(sig, length)
+            return self._chunked(self._sig_to_toks, sig, length, sig.shape[-1])
 
     @torch.no_grad()
     def sig_to_feats(self, sig, length=None):  # R/codec.py:68-77
-        sig, length = self._prep_sig(sig, length)
-        return self._sig_to_feats(sig, length)
+        with self._on(sig):
+            sig, length = self._prep_sig(sig, length)
+            return self._sig_to_feats(sig, length)
 
     @torch.no_grad()
     def sig_to_qfeats(self, sig, length=None):  # R/codec.py:79-88
-        sig, length = self._prep_sig(sig, length)
-        return self._sig_to_qfeats(sig, length)
+        with self._on(sig):
+            sig, length = self._prep_sig(sig, length)
+            return self._sig_to_qfeats(sig, length)
 
     @torch.no_grad()
     def toks_to_sig(self, toks, length=None):  # R/codec.py:90-100
-        sig = self._chunked(self._toks_to_sig, toks, length, toks.shape[1] * self._hop())
-        return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
+        with self._on(toks):
+            self._check_toks(toks)
+            sig = self._chunked(self._toks_to_sig, toks, length, toks.shape[1] * self._hop())
+            return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
 
     def _hop(self):
         """codec-rate samples per token frame (used only to size sub-batches)"""
@@ -89,11 +119,14 @@ class Codec(torch.nn.Module, ABC):
 
     @torch.no_grad()
     def toks_to_qfeats(self, toks, length=None):  # R/codec.py:102-108
-        return self._toks_to_qfeats(toks, length)
+        with self._on(toks):
+            self._check_toks(toks)
+            return self._toks_to_qfeats(toks, length)
 
     def feats_to_sig(self, feats, length=None):  # R/codec.py:109-119 (EnCodec / DAC / Mimi define no `_feats_to_sig`)
-        sig = self._feats_to_sig(feats, length)
-        return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
+        sig = self._feats_to_sig(feats, length)  # NotImplementedError for these three codecs, as in the reference
+        with self._on(sig):
+            return ops.resample(sig, self.orig_sample_rate, self.sample_rate)
 
     # ---- token augmentation (R/codec.py:121-180): the step right after the tokenizer in the downstream recipes.  Host-side
     # torch ops over `embs()` -- sampling is not on the hot path.

@@ -35,9 +35,27 @@ __device__ __forceinline__ float snake_fast(float x, float a, float ra) {
 struct FirstP {
     const float* x; const float* w; const float* bias; const float* alpha; const int* vlen;
     __nv_bfloat16* y; __nv_bfloat16* y_act;
+    __nv_bfloat16* y_lo; __nv_bfloat16* y_act_lo;   // optional lo planes: bf16(v - float(bf16(v)))
     long long y_bs, ya_bs;
     int T, K, pad_left, pad_mode, reflect_len, act;
 };
+
+// 8 values -> the 16 bytes of their bf16 roundings; with `lo` also the 16 bytes of the rounding residuals
+__device__ __forceinline__ void store8_split(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = pack2(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(hi) = make_uint4(q[0], q[1], q[2], q[3]);
+    if (lo) {
+        uint32_t r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&q[i]);
+            r[i] = pack2(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
+        }
+        *reinterpret_cast<uint4*>(lo) = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
 
 // block = (C/8) x 32 threads; one block pass = 32 time steps x C channels; a block owns TILE time steps.
 // The kernel was instruction-issue bound (ncu: 68 % issue slots, 265 instructions per 8 outputs against 1.9 GB of stores):
@@ -87,18 +105,14 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
             }
         }
         const long long off = (long long)t * C + grp * 8;
-        if (p.y) {
-            *reinterpret_cast<uint4*>(p.y + (long long)b * p.y_bs + off) =
-                make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
-        }
+        if (p.y) store8_split(acc, p.y + (long long)b * p.y_bs + off, p.y_lo ? p.y_lo + (long long)b * p.y_bs + off : nullptr);
         if (p.y_act) {
             float a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 a[c] = ACT == AC_ACT_ELU ? (acc[c] > 0.f ? acc[c] : exp2f(acc[c] * 1.4426950408889634f) - 1.0f)
                                          : (ACT == AC_ACT_SNAKE ? snake_fast(acc[c], al[c], ral[c]) : acc[c]);
-            *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + off) =
-                make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+            store8_split(a, p.y_act + (long long)b * p.ya_bs + off, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + off : nullptr);
         }
     }
 }
@@ -150,13 +164,15 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const LastP p) {
 }  // namespace
 
 extern "C" int ac_conv_first_bf16(const float* x, const float* w, const float* bias, const float* alpha, const int32_t* vlen,
-                                  void* y, void* y_act, int64_t y_bstride, int64_t y_act_bstride, int32_t batch, int32_t T,
-                                  int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len, int32_t act,
-                                  void* stream) {
+                                  void* y, void* y_act, void* y_lo, void* y_act_lo, int64_t y_bstride, int64_t y_act_bstride,
+                                  int32_t batch, int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode,
+                                  int32_t reflect_len, int32_t act, void* stream) {
     AC_REQUIRE(x && w && (y || y_act), "ac_conv_first_bf16: null pointer");
     AC_REQUIRE(batch > 0 && batch <= 65535 && T > 0 && K >= 1 && K <= MAXK, "ac_conv_first_bf16: bad sizes");
     AC_REQUIRE(act != AC_ACT_SNAKE || alpha, "ac_conv_first_bf16: snake needs alpha");
-    FirstP p{x, w, bias, alpha, vlen, (__nv_bfloat16*)y, (__nv_bfloat16*)y_act, y_bstride, y_act_bstride,
+    AC_REQUIRE((!y_lo || y) && (!y_act_lo || y_act), "ac_conv_first_bf16: lo plane without its hi plane");
+    FirstP p{x, w, bias, alpha, vlen, (__nv_bfloat16*)y, (__nv_bfloat16*)y_act, (__nv_bfloat16*)y_lo, (__nv_bfloat16*)y_act_lo,
+             y_bstride, y_act_bstride,
              T, K, pad_left, pad_mode, reflect_len < T ? T : reflect_len, act};
     dim3 grid((T + 2047) / 2048, batch);
     cudaStream_t s = (cudaStream_t)stream;

@@ -574,11 +574,16 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     const size_t fixed = 1024 /*align slack*/ + 36 * 8 /*barriers + tmem slot*/ + (size_t)act_mod * 4 * (d->act == AC_ACT_SNAKE ? 3 : 1) + 64;
     const long long m_tiles = (d->m_rows + TILE_M - 1) / TILE_M;
     TcParams p{};
-    bool found = false;
     const int sms = sm_count();
+    // The contraction block bk fixes the order in which the (hi, lo) products of a block are accumulated, i.e. the fp32
+    // rounding of the result.  It must not depend on the batch size or on the tile grouping G a tuner asks for (a clip's
+    // tokens would then depend on its neighbours): the canonical bk is the one the G = 1 search settles on -- a function of
+    // the layer shape alone -- and a grouped tiling is accepted only if it fits with that same bk.
+    auto search = [&](int g_only, int bk_only, bool use_hint) -> bool {
     // pass 0 insists on deep rings (>= 3 A stages and >= 4 W stages, or resident weights); pass 1 takes anything that fits
-    for (int pass = 0; pass < 2 && !found; ++pass) {
-        for (int bk = d->bk; bk >= 16 && !found; bk >>= 1) {
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int bk = d->bk; bk >= 16; bk >>= 1) {
+            if (bk_only > 0 && bk != bk_only) continue;
             bool ok = true;
             for (int s = 0; s < n_ms; ++s) ok &= ms[s].hi->c0 % bk == 0;  // a k-block never straddles two phases
             if (!ok) continue;
@@ -587,8 +592,9 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
             const size_t w_res_total = (size_t)num_kb * w_kb_bytes * (1 + w_split);
             const bool resident = n_tiles == 1 && n_tile == d->n_total && w_res_total <= 96 * 1024;
             for (int G : {4, 2, 1}) {
-                if (d->g_hint > 0 && G != d->g_hint) continue;
-                if (d->g_hint <= 0 && G > 1) {
+                if (g_only > 0 && G != g_only) continue;
+                if (use_hint && d->g_hint > 0 && G != d->g_hint) continue;
+                if (!(use_hint && d->g_hint > 0) && G > 1) {
                     if (G * n_tile * 2 > 512) continue;                                   // keep two accumulator stages when grouping
                     if ((m_tiles / G) * n_tiles * d->batch < 2LL * sms) continue;         // not enough tiles to fill the chip
                 }
@@ -630,10 +636,18 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
                 p.w_stage_bytes = w_stage; p.w_plane_bytes = w_plane;
                 p.w_kb_bytes = w_kb_bytes; p.w_res_plane = (uint32_t)((size_t)num_kb * w_kb_bytes);
                 p.w_resident = resident ? 1 : 0;
-                found = true;
-                break;
+                return true;
             }
         }
+    }
+    return false;
+    };
+    bool found = search(1, 0, false);
+    if (found) {
+        const int bk_canonical = p.bk;
+        // a grouped tiling (hinted or heuristic) with the canonical bk, else the G = 1 tiling just found -- unless a hint
+        // asked for a specific G that does not fit: then this variant is rejected (ConfigError, nothing launched)
+        if (!(d->g_hint == 1) && !search(0, bk_canonical, true)) found = d->g_hint > 0 ? false : search(1, bk_canonical, false);
     }
     AC_REQUIRE(found, "ac_conv_tc: no tiling fits shared memory (n_total %d k_total %d)", d->n_total, k_total);
     const int bk = p.bk;

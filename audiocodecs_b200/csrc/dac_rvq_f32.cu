@@ -88,6 +88,7 @@ dac_rvq_encode_kernel(const float* __restrict__ z, const float* __restrict__ w_i
                 const int i = besti[tid * (THREADS / FR) + l];
                 if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
             }
+            if ((unsigned)bi >= (unsigned)n_codes) bi = 0;  // all-NaN scores: code 0, gather in range
             sel[tid] = bi;
             if (r0 + tid < rows) codes[(r0 + tid) * code_stride + k] = (int64_t)bi;
             for (int d = 0; d < CD; ++d) {

@@ -19,6 +19,7 @@
 // Outputs (bf16 hi [+lo] planes for the next layer's GEMM, or act(h + skip) for the consumer conv) are
 // fire-and-forget global stores issued one step late, off the critical path.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -51,6 +52,7 @@ struct LstmTcParams {
     __nv_bfloat16* fin_lo;
     long long skip_bs, fin_bs;
     int fin_act, batch, steps;
+    int f16;    // operands (W_hh in tensor memory, h in shared memory) are fp16 instead of bf16
     long long* dbg;  // optional [steps][8] clock64 samples from cluster 0 / CTA 0 (profiling aid)
 };
 
@@ -168,7 +170,8 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         // whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers); one elected lane
         // issues the 32 tcgen05.mma of the step back to back
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_bf16(128, NB);
+        // kind::f16 instruction descriptor: operand format bits 7-9 (A) / 10-12 (B) = 1 for bf16, 0 for fp16
+        const uint32_t idesc = p.f16 ? (make_idesc_bf16(128, NB) & ~((7u << 7) | (7u << 10))) : make_idesc_bf16(128, NB);
         uint64_t desc_base = 0;
         desc_base |= (uint64_t)((B_KSTR >> 4) & 0x3FFF) << 16;  // leading byte offset = K-direction core-matrix stride
         desc_base |= (uint64_t)((B_NSTR >> 4) & 0x3FFF) << 32;  // stride byte offset = 8-row group stride
@@ -278,8 +281,9 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
                 c_state[i] = fg * c_state[i] + ig * gg;
                 h_prev[i] = og * fast_tanh(c_state[i]);
                 // operand layout of the slice: core matrix (k_grp = u/8, n_grp = b/8), row b%8, element u%8
-                *reinterpret_cast<__nv_bfloat16*>(hsl + (u >> 3) * B_KSTR + (b >> 3) * B_NSTR + (b & 7) * 16 + (u & 7) * 2) =
-                    __float2bfloat16(h_prev[i]);
+                uint8_t* hp = hsl + (u >> 3) * B_KSTR + (b >> 3) * B_NSTR + (b & 7) * 16 + (u & 7) * 2;
+                if (p.f16) *reinterpret_cast<__half*>(hp) = __float2half_rn(h_prev[i]);
+                else *reinterpret_cast<__nv_bfloat16*>(hp) = __float2bfloat16(h_prev[i]);
             }
             if (dbg) p.dbg[t * 8 + 3] = clock64();
             if (t + 1 < p.steps) {
@@ -333,6 +337,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     p.skip_bs = d->skip_bstride; p.fin_bs = d->final_bstride;
     p.fin_act = d->final_act; p.batch = d->batch; p.steps = d->steps;
     p.dbg = (long long*)d->dbg;
+    p.f16 = d->operand_fp16 ? 1 : 0;
 
     const int clusters = (d->batch + nbv - 1) / nbv;
     cudaLaunchConfig_t cfg{};

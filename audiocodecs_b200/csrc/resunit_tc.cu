@@ -670,14 +670,19 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     const int halo = (d->taps - 1) * d->dilation;
 
     RuParams p{};
-    bool found = false;
+    // The contraction blocks (bk of the A / X sources, bkh of the hidden tile) fix the order in which the (hi, lo) products are
+    // accumulated, i.e. the fp32 rounding of the result.  They must depend on the layer shape alone -- not on the batch size or
+    // on the (G, double-buffering) variant a tuner asks for, or a clip's tokens would depend on its neighbours: the canonical
+    // pair is the one the un-hinted G = 1 search settles on, and every other tiling is accepted only with that same pair.
+    auto search = [&](int g_only, int bk_only, int bkh_only, bool use_hint) -> bool {
     // pass 0: double-buffered hidden tile / acc1 with deep rings; pass 1: double-buffered, any rings; pass 2: single-buffered
-    for (int pass = 0; pass < 3 && !found; ++pass)
-        for (int bk = d->bk; bk >= 16 && !found; bk >>= 1)
-        for (int bkh = 64; bkh >= 16 && !found; bkh >>= 1) {
+    for (int pass = 0; pass < 3; ++pass)
+        for (int bk = d->bk; bk >= 16; bk >>= 1)
+        for (int bkh = 64; bkh >= 16; bkh >>= 1) {
             if (d->cin % bk || d->ch % bkh) continue;
+            if ((bk_only > 0 && bk != bk_only) || (bkh_only > 0 && bkh != bkh_only)) continue;
             const int dbl = pass < 2 ? 1 : 0;
-            if (d->dbl_hint >= 0 && dbl != d->dbl_hint) continue;
+            if (use_hint && d->dbl_hint >= 0 && dbl != d->dbl_hint) continue;
             const int chunks1 = d->cin / bk, hblocks = d->ch / bkh, xchunks = has_x ? d->cin / bk : 0;
             const int nkb1 = d->taps * chunks1;
             const uint32_t w1_kb = round_up((uint32_t)d->ch * bk * 2, 1024), w2h_kb = round_up((uint32_t)d->cout * bkh * 2, 1024),
@@ -685,10 +690,11 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
             const size_t w_res_total = (size_t)nkb1 * w1_kb * (1 + w1_split) + ((size_t)hblocks * w2h_kb + (size_t)xchunks * w2x_kb) * (1 + w2_split);
             const bool resident = w_res_total <= 64 * 1024;
             for (int G : {4, 2, 1}) {
-                if (d->g_hint > 0 && G != d->g_hint) continue;
+                if (g_only > 0 && G != g_only) continue;
+                if (use_hint && d->g_hint > 0 && G != d->g_hint) continue;
                 const int need_cols = G * ((1 + dbl) * d->ch + d->cout);
                 if (need_cols > 512) continue;
-                if (d->g_hint <= 0 && G > 1 && (m_tiles / G) * d->batch < 2LL * sms) continue;
+                if (!(use_hint && d->g_hint > 0) && G > 1 && (m_tiles / G) * d->batch < 2LL * sms) continue;
                 const int R = G * TILE_M + halo;
                 const int a_pieces = (R + 255) / 256, a_box = (int)round_up((R + a_pieces - 1) / a_pieces, 8);
                 const int x_pieces = (G * TILE_M + 255) / 256, x_box = G * TILE_M / x_pieces;
@@ -743,10 +749,17 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 p.h_blk_bytes = h_blk; p.h_plane_bytes = h_plane; p.h_stage_bytes = (uint32_t)h_stage;
                 p.dbl = dbl; p.acc1_stride = (uint32_t)G * d->ch;
                 p.tmem_cols = cols; p.acc2_col = (uint32_t)G * d->ch * (1 + dbl);
-                found = true;
-                break;
+                return true;
             }
         }
+    return false;
+    };
+    bool found = search(1, 0, 0, false);
+    if (found) {
+        const int bk_c = p.bk, bkh_c = p.bkh;
+        const bool hinted = d->g_hint > 0 || d->dbl_hint >= 0;
+        if (!search(0, bk_c, bkh_c, true)) found = hinted ? false : search(1, bk_c, bkh_c, false);
+    }
     AC_REQUIRE(found, "ac_resunit_tc: no tiling fits shared memory (cin %d ch %d cout %d taps %d)", d->cin, d->ch, d->cout, d->taps);
 
     RuMaps maps;

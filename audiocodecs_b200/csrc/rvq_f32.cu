@@ -104,7 +104,9 @@ rvq_encode_f32_kernel(const float* __restrict__ x, const float* __restrict__ cbs
                 const int oi = __shfl_xor_sync(0xffffffffu, ix, off);
                 if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
             }
-            if (cl == 0) sel[fg * 4 + i] = ix;
+            // a NaN residual never beats -inf: the index stays at its sentinel -> code 0 (the reference returns an arbitrary
+            // index there); the gather below must stay in range
+            if (cl == 0) sel[fg * 4 + i] = (unsigned)ix < (unsigned)n_codes ? ix : 0;
         }
         __syncthreads();
         // ---- emit code, subtract the selected codeword

@@ -33,7 +33,8 @@ _ARCH = {  # descript-audio-codec 1.0.0 model zoo: tag -> (encoder rates, decode
 
 class DAC(Codec):
     """`DAC(sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False)`; extra keywords
-    `state_dict` (transformers.DacModel key format, or descript's weight_g/weight_v format) and `precision`."""
+    `state_dict` (transformers.DacModel key format, or descript's weight_g/weight_v format) and `precision`
+    ("exact" / "bf16" / "fp32", see `Encodec`: "exact" is the tensor path whose encoder reproduces the reference's tokens)."""
 
     max_chunk_samples = 64 * 441000  # ~0.2 KB of live activations per sample on the tensor path
 
@@ -46,11 +47,14 @@ class DAC(Codec):
     W_SINGLE = r"res_unit.\.conv1"
 
     def __init__(self, sample_rate, orig_sample_rate=16000, mode="reconstruct", num_codebooks=8, latent=False,
-                 state_dict=None, precision="fp32", split_min_ch=512, split_res_min_ch=64, w_single=None):
+                 state_dict=None, precision="exact", split_min_ch=512, split_res_min_ch=64, w_single=None):
         super().__init__(sample_rate, orig_sample_rate, mode)
         self.w_single = w_single
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
+        if precision not in ("exact", "fp32", "bf16"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
+                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
+        self.tensor_path = precision != "fp32"
+        self.exact = precision == "exact"
         # activated tensors (MMA operands) / raw residual-stream tensors with >= this many channels travel as (hi, lo) bf16 planes
         self.split_min_ch = split_min_ch
         self.split_res_min_ch = split_res_min_ch
@@ -58,7 +62,7 @@ class DAC(Codec):
         self.vocab_size = 1024
         self.latent = latent
         self.precision = precision
-        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
+        self.compute_dtype = "bf16" if self.tensor_path else "f32"
         tag = f"{int(orig_sample_rate / 1000)}khz"  # R/audiocodecs/dac.py:55
         if tag not in _ARCH:
             raise ValueError(f"no DAC model for {tag}")
@@ -70,6 +74,12 @@ class DAC(Codec):
                 raise ImportError("`pip install descript-audio-codec` to use this module")
             state_dict = dac.DAC.load(str(dac.utils.download(model_type=tag))).state_dict()
         self._build(state_dict)
+
+    def _w_split(self, name):
+        # "exact": every encoder layer keeps the (hi, lo) weight pair (the tokens must be the reference's)
+        if self.exact and name.startswith("encoder"):
+            return True
+        return super()._w_split(name)
 
     # ------------------------------------------------------------------ packing
     def _conv(self, sd, prefix, stride=1, dilation=1, padding=0, snake=None, epi=EPI_NONE):
@@ -117,7 +127,7 @@ class DAC(Codec):
             dec.append(self._conv(sd, "decoder.conv2", padding=3, snake="decoder.snake1", epi=EPI_TANH))
             self._dec = dec
         self._tcw = []
-        if self.precision == "bf16":
+        if self.tensor_path:
             self._build_tc(sd)
         nq = sum(1 for k in sd if k.startswith("quantizer.quantizers.") and k.endswith(".codebook.weight"))
         q = "quantizer.quantizers.{}."
@@ -128,7 +138,7 @@ class DAC(Codec):
         self.register_buffer("b_out", stack(lambda p: sd[p + "out_proj.bias"].float()), persistent=False)
         self.register_buffer("codebooks", stack(lambda p: sd[p + "codebook.weight"].float()), persistent=False)                  # [S,1024,8]
         self.register_buffer("_err", torch.zeros(1, dtype=torch.int32), persistent=False)
-        if self.precision == "bf16" and self.mode != "decode":
+        if self.tensor_path and self.mode != "decode":
             self._build_rvq_proj()
 
     def _packed(self):
@@ -199,13 +209,13 @@ class DAC(Codec):
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
-    def _split(self, C):
-        return C >= self.split_min_ch
+    def _split(self, C, enc=False):
+        return (enc and self.exact) or C >= self.split_min_ch
 
-    def _split_res(self, C):
-        return C >= self.split_res_min_ch
+    def _split_res(self, C, enc=False):
+        return (enc and self.exact) or C >= self.split_res_min_ch
 
-    def _tc_run_units(self, units, x, xs, next_alpha, out_halo=(0, 0)):
+    def _tc_run_units(self, units, x, xs, next_alpha, out_halo=(0, 0), enc=False):
         """three DacResidualUnits (HF/dac:173-207): x raw, xs = snake1(x) -> (y raw, ys = next_alpha-snake(y)).  The k7
         conv reads its 7 dilated taps from ONE staged block of xs (zero padding = TMA out-of-bounds fill); the 1x1 conv
         adds the residual and writes the raw stream plus the activation its consumer applies."""
@@ -214,26 +224,29 @@ class DAC(Codec):
         for i, (a1, W7, d, a2, W1) in enumerate(units):
             last = i == len(units) - 1
             nxt = next_alpha if last else units[i + 1][0]
-            y = None if last else Act(B, L, C, dev, split=self._split_res(C))
+            y = None if last else Act(B, L, C, dev, split=self._split_res(C, enc))
             hl, hr = out_halo if last else (0, 0)
-            ys = Act(B, L, C, dev, hl=hl, hr=hr, split=self._split(C))
+            ys = Act(B, L, C, dev, hl=hl, hr=hr, split=self._split(C, enc))
             a = Src(xs, taps=7, dilation=d, shift=-3 * d)
 
             def unfused(a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
-                hs = Act(B, L, C, dev, split=self._split(C))
+                hs = Act(B, L, C, dev, split=self._split(C, enc))
                 tc.conv_tc(W7, [a], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
                 tc.conv_tc(W1, [Src(hs)], L, res=x, y=y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
 
             def fused(g, dbl, a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
                 return lambda: tc.resunit_tc(W7, W1, a, L, res=x, y=y, y_act=ys, act1=ACT_SNAKE, alpha1=a2.t, act2=ACT_SNAKE,
-                                             alpha2=nxt.t, h_split=self._split(C), g_hint=g, dbl_hint=dbl, name="resunit_tc")
+                                             alpha2=nxt.t, h_split=self._split(C, enc), g_hint=g, dbl_hint=dbl, name="resunit_tc")
 
-            # one fused launch (hidden tensor on chip) when both accumulators fit tensor memory, or two tap-GEMM launches:
-            # the measured-fastest variant per layer shape
+            # one fused launch (hidden tensor on chip) when both accumulators fit tensor memory, or two tap-GEMM launches.
+            # Encoder: fused whenever it fits -- a rule, because the two forms group the fp32 accumulation differently and a
+            # clip's tokens must not depend on the batch it was tuned in (the tuner only picks the bit-identical tile grouping /
+            # buffering).  Decoder: the measured-fastest form per layer shape (waveforms agree to ~1e-5 either way)
             variants = [("unfused", unfused)]
             if 2 * C <= 512:
-                variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)] + variants
-            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None), variants)
+                fv = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)]
+                variants = fv if enc else fv + variants
+            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc), variants)
             x, xs = y, ys
         return xs
 
@@ -241,21 +254,21 @@ class DAC(Codec):
         B, T = sig.shape
         dev = sig.device
         C = self._enc[0].cout
-        x = Act(B, T, C, dev, split=False)   # the Cin=1 edge kernel writes single planes
-        xs = Act(B, T, C, dev, split=False)
+        x = Act(B, T, C, dev, split=self._split_res(C, True) and self.exact)   # "bf16": the first layer's outputs stay single planes
+        xs = Act(B, T, C, dev, split=self._split(C, True) and self.exact)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xs, act=ACT_SNAKE, alpha=self._tenc[0][0][0][0].t)
         L = T
         for bi, (units, a_down, Wdown, s) in enumerate(self._tenc):
             p = math.ceil(s / 2)
             hr = -(p + L) % s
-            ys = self._tc_run_units(units, x, xs, a_down, out_halo=(p, hr))
+            ys = self._tc_run_units(units, x, xs, a_down, out_halo=(p, hr), enc=True)
             ys.fill_halo(PAD_ZERO)
             Lout = (L + 2 * p - 2 * s) // s + 1
             C = 2 * C
             nxt = self._tenc[bi + 1][0][0][0] if bi + 1 < len(self._tenc) else self._tenc_last[0]
             last = bi + 1 == len(self._tenc)
-            x = None if last else Act(B, Lout, C, dev, split=self._split_res(C))
-            xs = Act(B, Lout, C, dev, split=self._split(C))
+            x = None if last else Act(B, Lout, C, dev, split=self._split_res(C, True))
+            xs = Act(B, Lout, C, dev, split=self._split(C, True))
             tc.conv_tc(Wdown, [Src(ys, taps=2, origin=-p, phases=s, rows=(p + L + hr) // s)], Lout, y=x, y_act=xs, act=ACT_SNAKE,
                        alpha=nxt.t, name="down_tc")
             L = Lout
@@ -314,12 +327,12 @@ class DAC(Codec):
         return torch.einsum("kcd,khd->kch", self.codebooks[:K], self.w_out[:K]) + self.b_out[:K, None, :]
 
     def _encode_latents(self, sig):
-        if self.precision == "bf16":
+        if self.tensor_path:
             return self._encoder_tc(sig.contiguous())
         return self._stack(self._enc, sig.contiguous()[:, :, None])
 
     def _sig_to_toks(self, sig, length):  # R/audiocodecs/dac.py:94-100 (`length` is ignored by the reference)
-        if self.precision == "bf16":  # 8-dimensional RVQ chain on the projected latents (no 1024-wide residual)
+        if self.tensor_path:  # 8-dimensional RVQ chain on the projected latents (no 1024-wide residual)
             P = self._encoder_tc(sig.contiguous(), proj=True)
             return ops.dac_rvq_encode_proj(P, self.rvq_cconst, self.rvq_cross, self.cb_normed, self.cb_norm2, self.codebooks,
                                            self.num_codebooks)
@@ -343,6 +356,6 @@ class DAC(Codec):
         return ops.dac_rvq_decode(toks, self.codebooks[:K], self.w_out[:K], self.b_out[:K], err_flag=self._err)
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/dac.py:124-130
-        if self.precision == "bf16":
+        if self.tensor_path:
             return self._decoder_tc(self._toks_to_qfeats(toks, length))
         return self._stack(self._dec, self._toks_to_qfeats(toks, length))[:, :, 0]

@@ -13,11 +13,16 @@ from .tc import Act, Src, TcWeights
 __all__ = ["Encodec"]
 
 RATIOS = (8, 5, 4, 2)  # facebook/encodec_24khz upsampling_ratios (HF/encodec/configuration_encodec.py)
-SPLIT_MIN_CH = 128     # activations with >= this many channels travel as (hi, lo) bf16 pairs (precision)
+SPLIT_MIN_CH = 128     # precision="bf16": activations with >= this many channels travel as (hi, lo) bf16 pairs (DESIGN.md,
+                       # precision); precision="exact": every ENCODER activation does (three products per MAC)
 RAW_MAX_CH = 0         # residual blocks with <= this many channels take RAW x and apply their input ELU on chip (raw mode of
                        # ac_resunit_tc: the producer layer writes one tensor instead of a raw and an activated copy).  Measured at
                        # 64: producers 25-35 % faster, but the blocks themselves 1.8x slower (raw + activated blocks halve the ring
                        # depth that fits shared memory) -- a net loss of 0.8 ms per step, so it is off
+FUSED_MAX_CH = 64      # residual blocks with <= this many channels run as ONE fused launch (hidden tile on chip), wider ones as two
+                       # tap-GEMM launches (measured faster at 128 / 256 channels).  A rule, not a timing: the two forms group
+                       # the fp32 accumulation differently, so the choice must not depend on the batch size.  None = let the
+                       # tuner time one against the other (scripts/tune_report.py)
 _VALID_BW = (1.5, 3.0, 6.0, 12.0, 24.0)
 
 
@@ -27,6 +32,14 @@ class Encodec(Codec):
     Extra keyword `state_dict`: weights in `transformers.EncodecModel` key format.  When omitted the
     pretrained checkpoint is fetched exactly like the reference does (`EncodecModel.from_pretrained`,
     R/audiocodecs/encodec.py:51) and only its state dict is kept.
+
+    `precision`:
+      "exact" (default) tcgen05 tensor path whose ENCODER carries every activation and weight as a (hi, lo) bf16 pair
+              (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulate; fp16 LSTM recurrence): embeddings within ~2e-5 of the
+              fp32 reference, so the tokens equal the reference's wherever its top-2 distance gap exceeds 1e-4.  The
+              decoder is the "bf16" one (waveform SI-SNR >= 40 dB).
+      "bf16"  fastest: (hi, lo) pairs only where the waveform SI-SNR needs them; ~95 % of the tokens equal the reference's.
+      "fp32"  SIMT fp32 kernels (debugging / parity reference; ~15x slower).
     """
 
     # every layer keeps the (hi, lo) weight pair: with single-plane weights everywhere the decoder SI-SNR falls to 39.9 dB
@@ -36,16 +49,20 @@ class Encodec(Codec):
     W_SINGLE = None
 
     def __init__(self, sample_rate, orig_sample_rate=24000, mode="reconstruct", num_codebooks=8, use_vocos=False,
-                 state_dict=None, precision="bf16", w_single=None):
+                 state_dict=None, precision="exact", w_single=None):
         super().__init__(sample_rate, orig_sample_rate, mode)
         self.w_single = w_single
         if use_vocos:
             raise NotImplementedError("the Vocos decoder branch (R/audiocodecs/encodec.py:53-66) is outside this build")
         self.num_codebooks = num_codebooks
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
+        if precision not in ("exact", "bf16", "fp32"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
+                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
         self.precision = precision
-        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
+        self.tensor_path = precision != "fp32"
+        self.exact = precision == "exact"
+        self.enc_split_min = 0 if self.exact else SPLIT_MIN_CH
+        self.compute_dtype = "bf16" if self.tensor_path else "f32"
         self.use_vocos = use_vocos
         self.vocab_size = 1024
         tag = int(orig_sample_rate / 1000)
@@ -92,9 +109,13 @@ class Encodec(Codec):
             self._specs.append(spec)
             self.register_buffer(f"{name}_whh{l}", sd[f"{prefix}.lstm.weight_hh_l{l}"].float().contiguous(),
                                  persistent=False)
-            if self.precision == "bf16":
-                self.register_buffer(f"{name}_whh{l}_bf16", sd[f"{prefix}.lstm.weight_hh_l{l}"].to(torch.bfloat16).contiguous(),
-                                     persistent=False)
+            if self.tensor_path:
+                # fp16 operands for the recurrence (W_hh in tensor memory, h fed back as fp16): 11-bit mantissas at the
+                # cost of one product; |W_hh| <= 1/sqrt(512)-ish and |h| < 1 are far inside the fp16 range.  CPU emulation
+                # (scripts/exact_mode_emulation.py): tokens identical to the fp32 oracle's, against 99.94 % with bf16 operands
+                whh = sd[f"{prefix}.lstm.weight_hh_l{l}"].float()
+                assert whh.abs().max() < 6.0e4, "W_hh outside the fp16 range"
+                self.register_buffer(f"{name}_whh{l}_16", whh.to(torch.float16).contiguous(), persistent=False)
             layers.append((spec, f"{name}_whh{l}"))
         return layers
 
@@ -126,13 +147,13 @@ class Encodec(Codec):
             self._dec_last_noact = copy.copy(self._dec_last)
             self._dec_last_noact.act = ACT_NONE
             self._specs.append(self._dec_last_noact)
-        if self.precision == "bf16":
+        if self.tensor_path:
             self._build_tc(sd)
         nq = sum(1 for k in sd if k.startswith("quantizer.layers.") and k.endswith(".codebook.embed"))
         cb = torch.stack([sd[f"quantizer.layers.{k}.codebook.embed"].float() for k in range(nq)]).contiguous()
         self.register_buffer("codebooks", cb, persistent=False)                 # [32, 1024, 128]
         self.register_buffer("cb_norm", cb.pow(2).sum(-1).contiguous(), persistent=False)  # |E|^2, HF/encodec:367
-        if self.precision == "bf16":  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
+        if self.tensor_path:  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
             hi = cb.to(torch.bfloat16)
             self.register_buffer("cb_split", torch.stack([hi, (cb - hi.float()).to(torch.bfloat16)]).contiguous(), persistent=False)
         self.register_buffer("_sync_ws", torch.zeros(64, dtype=torch.int32), persistent=False)
@@ -167,13 +188,14 @@ class Encodec(Codec):
         self._tcw.append(tail)
         return k3, tail
 
-    def _tc_lstm(self, sd, prefix):
+    def _tc_lstm(self, sd, prefix, exact=False):
         out = []
         for l in range(2):
-            # single bf16 product for the input projection: the recurrence (bf16 h, bf16 W_hh) dominates the LSTM's error, a
-            # split here changes the decoder SI-SNR by < 0.1 dB (measured: 45.1 -> 45.1 dB, code match unchanged)
+            # decoder / "bf16" encoder: single bf16 product for the input projection (a split changes the decoder SI-SNR by
+            # < 0.1 dB: 45.1 -> 45.1 dB).  "exact" encoder: three products -- with one the embedding error is 1.8e-4 instead of
+            # 1.9e-5 and 0.15 % of the safe tokens flip (scripts/exact_mode_emulation.py)
             W = TcWeights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"],
-                          split=False)
+                          split=exact)
             self._tcw.append(W)
             out.append(W)
         return out
@@ -184,7 +206,7 @@ class Encodec(Codec):
             for r in reversed(RATIOS):
                 self._tenc.append((self._tc_resblock(sd, f"encoder.layers.{idx}"), self._tc_conv(sd, f"encoder.layers.{idx + 2}"), r))
                 idx += 3
-            self._tenc_lstm = self._tc_lstm(sd, f"encoder.layers.{idx}")
+            self._tenc_lstm = self._tc_lstm(sd, f"encoder.layers.{idx}", exact=self.exact)
             self._tenc_last = self._tc_conv(sd, f"encoder.layers.{idx + 2}")
         if self.mode != "encode":
             self._tdec_first = self._tc_conv(sd, "decoder.layers.0")
@@ -197,28 +219,29 @@ class Encodec(Codec):
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor-path execution
-    def _tc_run_lstm(self, Ws, whh, x: Act, final: Act):
-        """x raw [B,N,512] -> final = ELU(lstm(x) + x) (HF/encodec:236-249 + the following ELU)."""
+    def _tc_run_lstm(self, Ws, whh, x: Act, final: Act, exact=False):
+        """x raw [B,N,512] -> final = ELU(lstm(x) + x) (HF/encodec:236-249 + the following ELU).  exact: the input
+        projections read the (hi, lo) pairs of x / h0 (three products)."""
         B, N, C = x.B, x.L, x.C
         dev = x.buf.device
         pre = torch.empty((B, N, 4 * C), device=dev, dtype=torch.float32)
-        tc.conv_tc(Ws[0], [Src(x.hi_only())], N, y32=pre, name="lstm_ih_tc")
-        h0 = Act(B, N, C, dev, split=True)   # the lo plane matters for the skip-add of the last layer's h only
-        ops.lstm_tc(pre, getattr(self, whh[0] + "_bf16"), out=h0)
-        tc.conv_tc(Ws[1], [Src(h0.hi_only())], N, y32=pre, name="lstm_ih_tc")
+        tc.conv_tc(Ws[0], [Src(x if exact else x.hi_only())], N, y32=pre, name="lstm_ih_tc")
+        h0 = Act(B, N, C, dev, split=True)   # "bf16": the lo plane matters for the skip-add of the last layer's h only
+        ops.lstm_tc(pre, getattr(self, whh[0] + "_16"), out=h0)
+        tc.conv_tc(Ws[1], [Src(h0 if exact else h0.hi_only())], N, y32=pre, name="lstm_ih_tc")
         # the skip-add + ELU runs as its own HBM-bound pass: inside the recurrence kernel its loads/stores sat on the
         # per-step critical path (layer 1 took 3.8 ms against 2.4 ms for layer 0)
-        ops.lstm_tc(pre, getattr(self, whh[1] + "_bf16"), out=h0)
+        ops.lstm_tc(pre, getattr(self, whh[1] + "_16"), out=h0)
         ops.add_act_bf16(h0, x, final, ACT_ELU)
 
-    def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act):
+    def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act, split_min=SPLIT_MIN_CH):
         """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe)))).
         Either ONE fused launch with the hidden activation kept on chip (ac_resunit_tc; tile grouping and double
         buffering tuned per shape) or two tap-GEMM launches -- whichever measures faster for this layer shape.
         xe is None in raw mode (C <= RAW_MAX_CH): x itself carries the 2-row halo, the kernel applies the input ELU on
         chip and reads the raw rows of the same staged blocks for the shortcut."""
         B, L, C = x.B, x.L, x.C
-        hs = C // 2 >= SPLIT_MIN_CH
+        hs = C // 2 >= split_min
         if xe is None:
             x.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
             a = Src(x, taps=3, origin=-2, rows=L + 2)
@@ -241,33 +264,38 @@ class Encodec(Codec):
             return lambda: tc.resunit_tc(Wk3, Wtail, a, L, x=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
                                          name="resblock_tc")
 
-        variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)] + [("unfused", unfused)]
-        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None), variants)
+        variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
+        if FUSED_MAX_CH is None:
+            variants.append(("unfused", unfused))
+        elif C > FUSED_MAX_CH:
+            variants = [("unfused", unfused)]
+        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None, hs), variants)
 
     def _encoder_tc(self, sig, vlen=None):
         B, T = sig.shape
         dev = sig.device
         raw = 32 <= RAW_MAX_CH
-        x = Act(B, T, 32, dev, hl=2 if raw else 0)
-        xe = None if raw else Act(B, T, 32, dev, hl=2)
+        smin = self.enc_split_min
+        x = Act(B, T, 32, dev, hl=2 if raw else 0, split=32 >= smin)
+        xe = None if raw else Act(B, T, 32, dev, hl=2, split=32 >= smin)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU, vlen=vlen)
         L = T
         for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):
             C = x.C
             Lout = -(-L // r)
             extra = Lout * r - L
-            ye = Act(B, L, C, dev, hl=r, hr=extra, split=C >= SPLIT_MIN_CH)
-            self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
+            ye = Act(B, L, C, dev, hl=r, hr=extra, split=C >= smin)
+            self._tc_resblock_run(Wk3, Wtail, x, xe, ye, split_min=smin)
             ye.fill_halo(PAD_REFLECT, max(r, extra) + 1 if L <= max(r, extra) else 0)
             last = i == len(self._tenc) - 1
             raw = not last and 2 * C <= RAW_MAX_CH
-            x = Act(B, Lout, 2 * C, dev, hl=2 if raw else 0, split=2 * C >= SPLIT_MIN_CH)
-            xe = None if (last or raw) else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= SPLIT_MIN_CH)
+            x = Act(B, Lout, 2 * C, dev, hl=2 if raw else 0, split=2 * C >= smin)
+            xe = None if (last or raw) else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= smin)
             tc.conv_tc(Wdown, [Src(ye, taps=2, origin=-r, phases=r, rows=Lout + 1)], Lout, y=x, y_act=xe, act=ACT_ELU,
                        name="down_tc")
             L = Lout
         le = Act(B, L, x.C, dev, hl=6, split=True)
-        self._tc_run_lstm(self._tenc_lstm, [n for _, n in self._enc_lstm], x, le)
+        self._tc_run_lstm(self._tenc_lstm, [n for _, n in self._enc_lstm], x, le, exact=self.exact)
         le.fill_halo(PAD_REFLECT, 7 if L <= 6 else 0)
         emb = torch.empty((B, L, 128), device=dev, dtype=torch.float32)
         tc.conv_tc(self._tenc_last, [Src(le, taps=7, origin=-6, rows=L + 6)], L, y32=emb, name="conv_k7_tc")
@@ -353,18 +381,18 @@ class Encodec(Codec):
 
     def _sig_to_toks(self, sig, length):
         nq = self._num_quantizers()
-        enc = self._encoder_tc if self.precision == "bf16" else self._encoder
+        enc = self._encoder_tc if self.tensor_path else self._encoder
         emb = enc(sig, self._vlen(sig, length))
         B, N, D = emb.shape
         toks = torch.empty((B, N, nq), device=sig.device, dtype=torch.int64)
-        if self.precision == "bf16":
+        if self.tensor_path:
             ops.rvq_encode_tc(emb.view(B * N, D), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
         else:
             ops.rvq_encode(emb.view(B * N, D), self.codebooks, self.cb_norm, toks.view(B * N, nq), nq)
         return toks  # [B, N, K]
 
     def _sig_to_feats(self, sig, length):  # R/audiocodecs/encodec.py:97-117 (normalize=False: mask unused)
-        return (self._encoder_tc if self.precision == "bf16" else self._encoder)(sig)
+        return (self._encoder_tc if self.tensor_path else self._encoder)(sig)
 
     def _sig_to_qfeats(self, sig, length):  # R/audiocodecs/encodec.py:120-127
         return self._toks_to_qfeats(self._sig_to_toks(sig, length), length)
@@ -376,6 +404,6 @@ class Encodec(Codec):
         return q.view(B, N, -1)
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/encodec.py:130-141
-        if self.precision == "bf16":
+        if self.tensor_path:
             return self._decoder_tc(toks.to(torch.int64).contiguous())
         return self._decoder(self._toks_to_qfeats(toks, length))

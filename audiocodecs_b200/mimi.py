@@ -16,13 +16,15 @@ from .tc import Act, Src, TcWeights
 __all__ = ["Mimi"]
 
 RATIOS = (8, 6, 5, 4)  # MimiConfig().upsampling_ratios
-SPLIT_MIN_CH = 128     # activations with >= this many channels travel as (hi, lo) bf16 pairs (precision)
+SPLIT_MIN_CH = 128     # precision="bf16": activations with >= this many channels travel as (hi, lo) bf16 pairs (DESIGN.md,
+                       # precision); precision="exact": every ENCODER activation does
 HID, HEADS, HEAD_DIM, WINDOW, LAYERS = 512, 8, 64, 250, 8
 
 
 class Mimi(Codec):
     """`Mimi(sample_rate, mode="reconstruct", num_codebooks=8, latent=True)`; extra keywords `state_dict`
-    (`transformers.MimiModel` key format; default: fetch kyutai/mimi like the reference, mimi.py:45) and `precision`."""
+    (`transformers.MimiModel` key format; default: fetch kyutai/mimi like the reference, mimi.py:45) and `precision`
+    ("exact" / "bf16" / "fp32", see `Encodec`: "exact" is the tensor path whose encoder reproduces the reference's tokens)."""
 
     def _hop(self):
         return 1920
@@ -31,18 +33,22 @@ class Mimi(Codec):
     # blocks; decoder SI-SNR 51.8 -> 49.2 dB, step 61.6 -> 58.7 ms at 128 clips (scripts/weight_precision_probe.py)
     W_SINGLE = r"^decoder_transformer|^decoder\.layers.*block"
 
-    def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="fp32",
+    def __init__(self, sample_rate, mode="reconstruct", num_codebooks=8, latent=True, state_dict=None, precision="exact",
                  w_single=None):
         super().__init__(sample_rate, 24000, mode)
         self.w_single = w_single
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'bf16' (tcgen05 tensor path, fp32 accumulate) or 'fp32' (exact-parity SIMT path)")
+        if precision not in ("exact", "fp32", "bf16"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
+                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
+        self.tensor_path = precision != "fp32"
+        self.exact = precision == "exact"
+        self.enc_split_min = 0 if self.exact else SPLIT_MIN_CH
         self.num_codebooks = num_codebooks
         self.vocab_size = 2048
         self.latent = latent
         self.precision = precision
         self._rope_cache = {}
-        self.compute_dtype = "bf16" if precision == "bf16" else "f32"
+        self.compute_dtype = "bf16" if self.tensor_path else "f32"
         if state_dict is None:
             try:
                 from transformers import MimiModel
@@ -118,7 +124,7 @@ class Mimi(Codec):
             dec.append(self._conv(sd, f"decoder.layers.{idx}.conv", act=ACT_ELU))
             self._dec = dec
         self._tcw = []
-        if self.precision == "bf16":
+        if self.tensor_path:
             self._build_tc(sd)
         # quantizer: E = embed_sum / clamp(cluster_usage, 1e-5) (HF/mimi:1188-1195); semantic (1) then acoustic (31) codebooks
         cbs = []
@@ -132,7 +138,7 @@ class Mimi(Codec):
         cb = torch.stack(cbs).contiguous()
         self.register_buffer("codebooks", cb, persistent=False)                    # [32, 2048, 256]
         self.register_buffer("cb_norm", cb.pow(2).sum(-1).contiguous(), persistent=False)
-        if self.precision == "bf16":  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
+        if self.tensor_path:  # operand planes of the tensor-core distance GEMM: bf16(E), bf16(E - bf16(E))
             hi = cb.to(torch.bfloat16)
             self.register_buffer("cb_split", torch.stack([hi, (cb - hi.float()).to(torch.bfloat16)]).contiguous(), persistent=False)
         inv_freq = 1.0 / (10000.0 ** (torch.arange(0, HEAD_DIM, 2, dtype=torch.int64).float() / HEAD_DIM))  # HF/mimi:560-562
@@ -198,11 +204,11 @@ class Mimi(Codec):
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
-    def _tc_resblock(self, Wk3, Wk1, x, xe, ye):
+    def _tc_resblock(self, Wk3, Wk1, x, xe, ye, split_min=SPLIT_MIN_CH):
         """MimiResnetBlock (HF/mimi:412-451), identity shortcut, causal zero padding (TMA out-of-bounds fill):
         x raw, xe = ELU(x) -> ye = ELU(x + conv_k1(ELU(conv_k3(xe))))."""
         B, L, C = x.B, x.L, x.C
-        hs = C // 2 >= SPLIT_MIN_CH
+        hs = C // 2 >= split_min
         a = Src(xe, taps=3, shift=-2)
 
         def unfused():
@@ -214,10 +220,13 @@ class Mimi(Codec):
             return lambda: tc.resunit_tc(Wk3, Wk1, a, L, res=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
                                          name="resblock_tc")
 
+        # fused (hidden activation on chip) whenever the accumulators fit tensor memory (measured faster at 64-256 channels),
+        # else two launches.  A rule, not a timing: the two forms group the fp32 accumulation differently, and a clip's tokens
+        # must not depend on the batch it is tuned in; the tuner only picks the tile grouping / buffering (bit-identical)
         variants = [("unfused", unfused)]
-        if C <= 256:  # fused (hidden activation on chip) when the accumulators fit tensor memory; measured-fastest variant wins
-            variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)] + variants
-        tc.autotune(("mimi_resblock", B, L, C), variants)
+        if C <= 256:
+            variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
+        tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs), variants)
 
     def _tc_transformer(self, layers, tws, h):
         """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,
@@ -249,19 +258,20 @@ class Mimi(Codec):
         B, T = sig.shape
         dev = sig.device
         C = self._enc[0].cout
-        x = Act(B, T, C, dev)
-        xe = Act(B, T, C, dev)
+        smin = self.enc_split_min
+        x = Act(B, T, C, dev, split=C >= smin)
+        xe = Act(B, T, C, dev, split=C >= smin)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU)
         L = T
         for i, (Wk3, Wk1, Wdown, r) in enumerate(self._tenc):
             Lout = -(-L // r)
-            ye = Act(B, L, C, dev, hr=Lout * r - L, split=C >= SPLIT_MIN_CH)
-            self._tc_resblock(Wk3, Wk1, x, xe, ye)
+            ye = Act(B, L, C, dev, hr=Lout * r - L, split=C >= smin)
+            self._tc_resblock(Wk3, Wk1, x, xe, ye, split_min=smin)
             ye.fill_halo(PAD_ZERO)
             C = 2 * C
             last = i == len(self._tenc) - 1
-            x = None if last else Act(B, Lout, C, dev, split=C >= SPLIT_MIN_CH)
-            xe = Act(B, Lout, C, dev, split=C >= SPLIT_MIN_CH)
+            x = None if last else Act(B, Lout, C, dev, split=C >= smin)
+            xe = Act(B, Lout, C, dev, split=C >= smin)
             # kernel 2r / stride r causal conv: 2 taps over the r-phase view, tap 0 = the previous view row (zero for row 0)
             tc.conv_tc(Wdown, [Src(ye, taps=2, shift=-1, phases=r, rows=Lout)], Lout, y=x, y_act=xe, act=ACT_ELU, name="down_tc")
             L = Lout
@@ -315,7 +325,7 @@ class Mimi(Codec):
 
     def _embeddings(self, sig, want_act=False):
         """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
-        if self.precision == "bf16":
+        if self.tensor_path:
             h = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
             # `downsample` (HF/mimi:1419-1431): k4 s2 causal conv, replicate padding 2 left (+1 right for an odd length), as a
             # 2-tap GEMM over the 2-phase view of the padded split-bf16 copy; fp32 out
@@ -354,7 +364,7 @@ class Mimi(Codec):
     def _sig_to_toks(self, sig, length):
         K = self.num_codebooks
         self._check_k(K)
-        if self.precision == "bf16":
+        if self.tensor_path:
             emb, ea = self._embeddings(sig, want_act=True)
             B, N, _ = emb.shape
             toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
@@ -369,7 +379,7 @@ class Mimi(Codec):
             toks = torch.empty((B, N, K), device=sig.device, dtype=torch.int64)
             xs = ops.conv(self._semantic_in, emb)
             xa = ops.conv(self._acoustic_in, emb) if K > 1 else None
-        if self.precision == "bf16":  # tcgen05 distance GEMM + exact fp32 re-score (same decisions as the fp32 kernel)
+        if self.tensor_path:  # tcgen05 distance GEMM + exact fp32 re-score (same decisions as the fp32 kernel)
             ops.rvq_encode_tc(xs.view(B * N, -1), self.cb_split, self.codebooks, self.cb_norm, toks.view(B * N, K), 1, code_offset=0,
                               stage0=0, metric=1)
             if K > 1:
@@ -398,7 +408,7 @@ class Mimi(Codec):
         return out
 
     def _toks_to_sig(self, toks, length):  # R/audiocodecs/mimi.py:144-148 ; HF/mimi:1613-1631
-        if self.precision == "bf16":  # gather-sums straight into split-bf16 operands, both output_proj as one GEMM
+        if self.tensor_path:  # gather-sums straight into split-bf16 operands, both output_proj as one GEMM
             B, N, K = toks.shape
             self._check_k(K)
             toks = toks.to(torch.int64).contiguous()
@@ -416,7 +426,7 @@ class Mimi(Codec):
         else:
             z = self._toks_to_qfeats(toks, length)
         z = ops.upsample_dw(z, self.up_w)
-        if self.precision == "bf16":
+        if self.tensor_path:
             return self._decoder_tc(self._tc_transformer(self._dec_tr, self._tdec_tr, z))
         z = self._run_transformer(self._dec_tr, z)
         return self._seanet(self._dec, z)[:, :, 0]

@@ -189,6 +189,8 @@ def conv_first_bf16(spec, sig, y=None, y_act=None, act=ACT_NONE, vlen=None, pad_
     _lib.check(_lib.lib().ac_conv_first_bf16(
         _ptr(sig), _ptr(spec.w), _ptr(spec.bias), _ptr(alpha), _ptr(vlen),
         ctypes.c_void_p(y.row_ptr(0)) if y is not None else None, ctypes.c_void_p(y_act.row_ptr(0)) if y_act is not None else None,
+        ctypes.c_void_p(y.lo_ptr(0)) if (y is not None and y.lo is not None) else None,
+        ctypes.c_void_p(y_act.lo_ptr(0)) if (y_act is not None and y_act.lo is not None) else None,
         y.bstride if y is not None else 0, y_act.bstride if y_act is not None else 0, B, T, C, K, pad_left, spec.pad_mode,
         reflect_len, act, _stream()), "ac_conv_first_bf16")
     if _PROFILER:
@@ -212,7 +214,8 @@ def conv_last_bf16(spec, x_act, epi=EPI_NONE, pad_left=None):
 
 
 def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE, dbg=None):
-    """tensor-core LSTM recurrence: pre [B,T,2048] fp32; out / skip / final are tc.Act (bf16 hi[/lo] planes)."""
+    """tensor-core LSTM recurrence: pre [B,T,2048] fp32; out / skip / final are tc.Act (bf16 hi[/lo] planes).
+    w_hh_bf16: [2048,512] bf16, or fp16 (then h is fed back as fp16 too: 11-bit operands)."""
     from ._lib import AcLstmTcDesc
     _need_cuda(pre, w_hh_bf16)
     B, T, C4 = pre.shape
@@ -227,6 +230,8 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE,
         d.final_hi, d.final_lo, d.final_bstride = final.row_ptr(0), final.lo_ptr(0), final.bstride
     d.final_act, d.batch, d.steps, d.hidden = final_act, B, T, C4 // 4
     d.dbg = _ptr(dbg)
+    assert w_hh_bf16.dtype in (torch.bfloat16, torch.float16) and w_hh_bf16.is_contiguous()
+    d.operand_fp16 = int(w_hh_bf16.dtype == torch.float16)
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
     if _PROFILER:

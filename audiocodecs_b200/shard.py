@@ -18,6 +18,16 @@ def shard_range(n, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def _codec_device(codec, fallback):
+    """the device holding the codec's weights (an nn.Module has no .device attribute); test doubles without buffers fall
+    back to the input's device"""
+    bufs = getattr(codec, "buffers", None)
+    if bufs is not None:
+        for b in bufs():
+            return b.device
+    return getattr(codec, "device", None) or fallback
+
+
 def _world(group):
     if not (dist.is_available() and dist.is_initialized()):
         return 0, 1
@@ -44,7 +54,7 @@ def tokenize_sharded(codec, sig, length=None, group=None, gather=True):
     GPU; with gather=True every rank returns all B clips' tokens [B, N, K] (int64), else only its own slice."""
     rank, world = _world(group)
     a, b = shard_range(sig.shape[0], rank, world)
-    dev = getattr(codec, "device", None) or sig.device
+    dev = _codec_device(codec, sig.device)
     local_len = None if length is None else length[a:b].to(dev)
     toks = codec.sig_to_toks(sig[a:b].to(dev), local_len) if b > a else None
     if toks is None:  # more ranks than clips: learn the token shape from a peer through the padded gather
@@ -62,7 +72,7 @@ def detokenize_sharded(codec, toks, length=None, group=None, gather=True):
     """`toks` [B, N, K] global -> waveforms; same sharding as `tokenize_sharded`."""
     rank, world = _world(group)
     a, b = shard_range(toks.shape[0], rank, world)
-    dev = getattr(codec, "device", None) or toks.device
+    dev = _codec_device(codec, toks.device)
     if b == a:
         raise ValueError("detokenize_sharded needs at least one clip per rank")
     sig = codec.toks_to_sig(toks[a:b].to(dev), None if length is None else length[a:b].to(dev))

@@ -208,6 +208,7 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
 _TUNED = {}
 TUNE = True  # False: always take the first variant
 TUNE_ERRORS = []  # (key, variant, message) of variants that failed with something other than a configuration error
+TUNE_LOG = []     # (key, {variant: best ms}) of every tuned key, for reports (scripts/tune_report.py)
 
 
 def autotune(key, variants):
@@ -216,7 +217,10 @@ def autotune(key, variants):
     the winner; a variant whose tiling does not fit (`_lib.ConfigError`, nothing launched) is skipped; a variant that fails to
     launch is skipped too but recorded in TUNE_ERRORS and named if no variant works.  Later calls dispatch straight to the winner.
     Measured choices replace hand-written heuristics: which tiling wins depends on the layer shape in ways (TMA row
-    granularity, weight re-streaming per tile, epilogue / tensor-pipe balance) that the profiles only explained afterwards."""
+    granularity, weight re-streaming per tile, epilogue / tensor-pipe balance) that the profiles only explained afterwards.
+    The variants of one key must be BIT-IDENTICAL in their results (same contraction blocks and product order -- the kernels
+    pin those per layer shape; only the tile grouping / buffering differs), so that the winner, which may differ between batch
+    sizes, ranks and runs, never changes a token."""
     name = _TUNED.get(key)
     if name is None:
         if not TUNE or len(variants) == 1:
@@ -253,6 +257,7 @@ def autotune(key, variants):
             if not times:
                 raise RuntimeError(f"audiocodecs_b200: no variant of {key} could be launched {TUNE_ERRORS[-3:]}")
             name = min(times, key=times.get)
+            TUNE_LOG.append((key, dict(times)))
         _TUNED[key] = name
     for vname, fn in variants:
         if vname == name:

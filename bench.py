@@ -57,14 +57,14 @@ def make_state_dict(codec):
             "mimi": weights.mimi_state_dict}[codec](0)
 
 
-def make_codec(codec, sd):
+def make_codec(codec, sd, precision="exact"):
     import audiocodecs_b200 as A
     wl = WORKLOADS[codec]
     if codec in ("encodec", "encodec32"):
-        return A.Encodec(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd)
+        return A.Encodec(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision=precision)
     if codec == "dac":
-        return A.DAC(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision="bf16")
-    return A.Mimi(wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision="bf16")
+        return A.DAC(wl["sr"], wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision=precision)
+    return A.Mimi(wl["sr"], num_codebooks=wl["K"], state_dict=sd, precision=precision)
 
 
 def oracle_fns(codec):
@@ -129,7 +129,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     B, T = args.batch or wl["batch"], wl["sr"] * SECONDS
     sd = make_state_dict(args.codec)
-    codec = make_codec(args.codec, sd).eval().to(dev)
+    codec = make_codec(args.codec, sd, args.precision).eval().to(dev)
     g = torch.Generator().manual_seed(999 + rank)
     host_sig = (torch.randn(B, T, generator=g) * 0.1).pin_memory()
     sig = host_sig.to(dev)
@@ -244,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": codec.compute_dtype, "data": "synthetic",
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "clip_seconds": SECONDS, "sample_rate": wl["sr"],
-                   "num_codebooks": wl["K"], "weights": "random-init (seed 0, matched-moment codebooks)",
+                   "num_codebooks": wl["K"], "precision": args.precision, "weights": "random-init (seed 0, matched-moment codebooks)",
                    "l2": "activations per step exceed the 126 MB L2 many times over (inputs_exceed_l2)",
                    "parallelism": f"clip-sharded x{world}, no data-path collective"},
         "e2e": {"value": round(e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": B * T * 4 * world,
@@ -326,6 +326,8 @@ def main():
     ap.add_argument("--codec", default="encodec", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU clips (default: the BASELINE workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="exact", choices=["exact", "bf16", "fp32"],
+                    help="exact (default): tensor path whose tokens equal the reference's; bf16: fastest tensor path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AC_ABI_VERSION 1
+#define AC_ABI_VERSION 2
 #define AC_API __attribute__((visibility("default")))
 
 /* padding modes of the input row index */
@@ -107,6 +107,8 @@ typedef struct ac_lstm_tc_desc {
     int64_t skip_bstride, final_bstride;
     int32_t final_act, batch, steps, hidden;
     void* dbg;                 /* optional int64 [steps][8] clock samples (profiling aid), else NULL */
+    int32_t operand_fp16;      /* 1: w_hh_bf16 holds IEEE fp16 and h[t-1] is fed back as fp16 (11-bit mantissas: |W_hh| and |h| < 1
+                                  sit well inside the fp16 range) -- one product at 2^-12 instead of 2^-9 operand rounding */
 } ac_lstm_tc_desc;
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
 
@@ -284,15 +286,17 @@ AC_API int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, int3
  * Edge layers of the bf16 pipeline (HBM-bound, SIMT):
  * first: y[b][t][c] = bias[c] + sum_j w[j][c] * x[b][pad(t + j - pad_left)]   (Cin = 1; fp32 waveform in, bf16 out:
  *        raw copy `y` and/or `y_act` = act(y), act = ELU or Snake(alpha));  C in {32, 64, 96}, K <= 8.
+ *        y_lo / y_act_lo: optional lo planes bf16(v - float(bf16(v))) of the same layout (the "exact" precision mode
+ *        carries every activation as a (hi, lo) pair).
  *        vlen: optional per-clip valid length (padding mask, R/audiocodecs/encodec.py:84-89).
  * last : y[b][t] = epi(bias + sum_j sum_c w[j][c] * x[b][pad(t + j - pad_left)][c])   (Cout = 1; bf16 in, fp32 out).
  * Replace the first/last conv of EncodecEncoder/Decoder (HF/encodec:289,341), MimiEncoder/Decoder (HF/mimi:461,1169),
  * DacEncoder/Decoder (HF/dac:449,434-437).
  */
 AC_API int ac_conv_first_bf16(const float* x, const float* w, const float* bias, const float* alpha, const int32_t* vlen,
-                              void* y, void* y_act, int64_t y_bstride, int64_t y_act_bstride, int32_t batch, int32_t T,
-                              int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len, int32_t act,
-                              void* stream);
+                              void* y, void* y_act, void* y_lo, void* y_act_lo, int64_t y_bstride, int64_t y_act_bstride,
+                              int32_t batch, int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode,
+                              int32_t reflect_len, int32_t act, void* stream);
 AC_API int ac_conv_last_bf16(const void* x, const float* w, const float* bias, float* y, int64_t x_bstride, int32_t batch,
                              int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len,
                              int32_t epi, void* stream);

@@ -9,12 +9,13 @@ from oracle import weights
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 which = sys.argv[2] if len(sys.argv) > 2 else "encodec"
 dev = torch.device("cuda:0")
+prec = os.environ.get("AC_PRECISION", "exact")
 if which == "encodec":
-    codec, sr, B = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0)), 24000, 64
+    codec, sr, B = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0), precision=prec), 24000, 64
 elif which == "dac":
-    codec, sr, B = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision="bf16"), 44100, 64
+    codec, sr, B = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision=prec), 44100, 64
 else:
-    codec, sr, B = A.Mimi(24000, num_codebooks=8, state_dict=weights.mimi_state_dict(0), precision="bf16"), 24000, 128
+    codec, sr, B = A.Mimi(24000, num_codebooks=8, state_dict=weights.mimi_state_dict(0), precision=prec), 24000, 128
 B = int(sys.argv[3]) if len(sys.argv) > 3 else B
 codec = codec.eval().to(dev)
 sig = (torch.randn(B, sr * 10, generator=torch.Generator().manual_seed(999)) * 0.1).to(dev)

@@ -59,15 +59,19 @@ def test_end_to_end_code_match_report(encodec_sd, dev):
     toks = codec.sig_to_toks(sig.to(dev))
     assert toks.shape == ref.shape and toks.dtype == torch.int64
     per_stage = [(toks.cpu()[..., k] == ref[..., k]).float().mean().item() for k in range(8)]
-    print("bf16 end-to-end code match per stage:", [round(x, 4) for x in per_stage])
-    assert per_stage[0] > 0.85 and min(per_stage) > 0.5
+    m_safe, tie, m_all = code_report(toks, ref, gaps)
+    print("bf16 end-to-end code match per stage:", [round(x, 4) for x in per_stage], f"safe {m_safe:.4f} all {m_all:.4f} near-ties {tie:.4f}")
+    # measured (and reproduced by scripts/exact_mode_emulation.py): 0.985 at stage 0 decaying to 0.924 at stage 7, 0.951 overall
+    assert per_stage[0] > 0.965 and min(per_stage) > 0.90 and m_safe > 0.93
     rec = codec.toks_to_sig(toks)
     assert tuple(rec.shape) == (4, 48000) and torch.isfinite(rec).all()
 
 
+@pytest.mark.parametrize("op_dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12), (70, 9)])
-def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T):
-    """tcgen05 cluster LSTM (bf16 W_hh and h operands, fp32 accumulate / cell state) vs the oracle's explicit loop."""
+def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T, op_dtype, tol):
+    """tcgen05 cluster LSTM (fp16 -- the shipped configuration -- or bf16 W_hh and h operands, fp32 accumulate / cell state)
+    vs the oracle's explicit loop."""
     from audiocodecs_b200 import ops
     from audiocodecs_b200.tc import Act
     g = torch.Generator().manual_seed(77)
@@ -88,16 +92,16 @@ def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T):
     sk = Act(B, T, C, dev, split=True)
     sk.buf.copy_(skip.to(torch.bfloat16)); sk.lo.copy_((skip - skip.to(torch.bfloat16).float()).to(torch.bfloat16))
     fin = Act(B, T, C, dev, hl=3, split=True)
-    ops.lstm_tc(pre.to(dev), w_hh.to(torch.bfloat16).to(dev), out=out, skip=sk, final=fin, final_act=ops.ACT_ELU)
+    ops.lstm_tc(pre.to(dev), w_hh.to(op_dtype).to(dev), out=out, skip=sk, final=fin, final_act=ops.ACT_ELU)
     torch.cuda.synchronize()
     got = out.buf.float().cpu() + out.lo.float().cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
-    print(f"lstm_tc max|err| {err:.2e} (B={B}, T={T})")
-    assert err < 2e-2, err
+    print(f"lstm_tc {op_dtype} max|err| {err:.2e} (B={B}, T={T})")
+    assert err < tol, err
     ref_fin = torch.nn.functional.elu(ref + skip)
     got_fin = (fin.data().float() + fin.lo[:, 3:3 + T].float()).cpu()
-    assert (got_fin - ref_fin).abs().max().item() < 3e-2
+    assert (got_fin - ref_fin).abs().max().item() < 1.5 * tol
 
 
 def test_host_pipeline_matches_direct_calls(encodec_sd, dev):
@@ -118,7 +122,7 @@ def test_cuda_graph_replay_matches_eager(encodec_sd, dev):
     """GraphedCodec: the captured tokenize / detokenize graphs give the eager calls' results bit for bit, also on new inputs
     of the captured shape, and refuse other shapes."""
     import audiocodecs_b200 as A
-    codec = A.Encodec(24000, 24000, num_codebooks=8, state_dict=encodec_sd).eval().to(dev)
+    codec = A.Encodec(24000, 24000, num_codebooks=8, state_dict=encodec_sd, precision="bf16").eval().to(dev)
     sig = make_input(5, 2, 9600).to(dev)
     g = A.GraphedCodec(codec, sig)
     for seed in (5, 6, 7):

@@ -19,7 +19,7 @@ def dev():
 def test_mimi_golden_cases(mimi_sd, mimi_golden, dev, case):
     import audiocodecs_b200 as A
     c = mimi_golden["cases"][case]
-    codec = A.Mimi(c["sample_rate"], num_codebooks=c["K"], state_dict=mimi_sd).eval().to(dev)
+    codec = A.Mimi(c["sample_rate"], num_codebooks=c["K"], state_dict=mimi_sd, precision="fp32").eval().to(dev)
     sig = make_input(c["seed"], c["B"], c["T"]).to(dev)
     toks = codec.sig_to_toks(sig)
     ref_toks = c["toks"].long()
@@ -37,7 +37,7 @@ def test_mimi_golden_cases(mimi_sd, mimi_golden, dev, case):
 def test_mimi_transformer_pieces(mimi_sd, dev):
     """attention (RoPE + sliding window, T > window) and LayerNorm vs the oracle on a long sequence."""
     import audiocodecs_b200 as A
-    codec = A.Mimi(24000, num_codebooks=8, state_dict=mimi_sd).eval().to(dev)
+    codec = A.Mimi(24000, num_codebooks=8, state_dict=mimi_sd, precision="fp32").eval().to(dev)
     h = torch.randn(2, 300, 512, generator=torch.Generator().manual_seed(3))
     with torch.no_grad():
         ref = mimi_ref.transformer(mimi_sd, "encoder_transformer", h)
@@ -47,12 +47,12 @@ def test_mimi_transformer_pieces(mimi_sd, dev):
 
 def test_mimi_qfeats_and_errors(mimi_sd, dev):
     import audiocodecs_b200 as A
-    codec = A.Mimi(24000, num_codebooks=8, state_dict=mimi_sd).eval().to(dev)
+    codec = A.Mimi(24000, num_codebooks=8, state_dict=mimi_sd, precision="fp32").eval().to(dev)
     toks = torch.randint(0, 2048, (2, 11, 8), generator=torch.Generator().manual_seed(2))
     ref = mimi_ref.toks_to_qfeats(mimi_sd, toks)
     got = codec.toks_to_qfeats(toks.to(dev)).cpu()
     assert (got - ref).abs().max().item() < 1e-5
-    bad = A.Mimi(24000, num_codebooks=33, state_dict=mimi_sd).eval().to(dev)
+    bad = A.Mimi(24000, num_codebooks=33, state_dict=mimi_sd, precision="fp32").eval().to(dev)
     with pytest.raises(ValueError):
         bad.sig_to_toks(torch.zeros(1, 4000, device=dev))
 
@@ -61,7 +61,7 @@ def test_mimi_qfeats_and_errors(mimi_sd, dev):
 def test_dac_golden_cases(dac_sd, dac_golden, dev, case):
     import audiocodecs_b200 as A
     c = dac_golden["cases"][case]
-    codec = A.DAC(c["sample_rate"], 44100, num_codebooks=c["K"], state_dict=dac_sd).eval().to(dev)
+    codec = A.DAC(c["sample_rate"], 44100, num_codebooks=c["K"], state_dict=dac_sd, precision="fp32").eval().to(dev)
     sig = make_input(c["seed"], c["B"], c["T"]).to(dev)
     toks = codec.sig_to_toks(sig)
     ref_toks = c["toks"].long()
@@ -78,7 +78,7 @@ def test_dac_golden_cases(dac_sd, dac_golden, dev, case):
 def test_dac_rvq_kernels_on_oracle_latents(dac_sd, dev):
     import audiocodecs_b200 as A
     from audiocodecs_b200 import ops
-    codec = A.DAC(44100, 44100, num_codebooks=9, state_dict=dac_sd).eval().to(dev)
+    codec = A.DAC(44100, 44100, num_codebooks=9, state_dict=dac_sd, precision="fp32").eval().to(dev)
     z = torch.randn(3, 1024, 50, generator=torch.Generator().manual_seed(9)) * 0.2
     with torch.no_grad():
         codes, gaps, zq = dac_ref.rvq_encode(dac_sd, z, 9, return_gaps=True)
