@@ -39,8 +39,16 @@ class Codec(torch.nn.Module, ABC):
             return self.sig_to_toks(input, length)
         if self.mode == "decode":
             return self.toks_to_sig(input, length)
-        toks = self.sig_to_toks(input, length)
-        return self.toks_to_sig(toks, length)
+        return self.reconstruct(input, length)
+
+    @torch.no_grad()
+    def reconstruct(self, sig, length=None):
+        """toks_to_sig(sig_to_toks(sig)) (mode="reconstruct", R/codec.py:52-54) without the token range check -- the tokens
+        come from this codec's own encoder -- so nothing synchronises the host between the two halves."""
+        toks = self.sig_to_toks(sig, length)
+        with self._on(toks):
+            out = self._chunked(self._toks_to_sig, toks, length, toks.shape[1] * self._hop())
+            return ops.resample(out, self.orig_sample_rate, self.sample_rate)
 
     def _on(self, t):
         """device guard: every launch of a call goes to the device (and its current stream) that holds the input -- the C-ABI

@@ -4,6 +4,7 @@ Same constructor arguments and tensor shapes.  The arithmetic of descript-audio-
 reference; twin: HF/dac/modeling_dac.py) is replaced by the sm_100a kernels of this package.
 """
 import math
+import re
 
 import torch
 
@@ -24,6 +25,52 @@ class TcAlpha:
     def apply(self, fn):
         self.t = fn(self.t)
 
+def descript_to_hf_keys(sd):
+    """State dict of a descript-audio-codec 1.0.0 `dac.DAC` (nn.Sequential indices: `encoder.block.N...`,
+    `decoder.model.N...`, old-style `weight_g / weight_v`; dac/model/dac.py Encoder / EncoderBlock / ResidualUnit / Decoder /
+    DecoderBlock) -> the `transformers.DacModel` names this wrapper packs from (HF/dac/modeling_dac.py:173-262,405-472).
+    The weight-norm pairs are kept as they are (`packing.fold_weight_norm` folds either spelling); quantizer keys are equal
+    in both layouts.  A dict that is already in HF format is returned unchanged."""
+    if not any(k.startswith("decoder.model.") or re.match(r"encoder\.block\.\d+\.block\.", k) for k in sd):
+        return sd
+    unit = {"0": "snake1", "1": "conv1", "2": "snake2", "3": "conv2"}
+    out = {}
+    for k, v in sd.items():
+        p = k.split(".")
+        if p[0] == "encoder" and p[1] == "block":
+            i = int(p[2])
+            if i == 0:
+                new = ["encoder", "conv1"] + p[3:]
+            elif i == 5:
+                new = ["encoder", "snake1"] + p[3:]
+            elif i == 6:
+                new = ["encoder", "conv2"] + p[3:]
+            else:  # EncoderBlock i-1: block.{0,1,2} residual units, block.3 snake, block.4 strided conv
+                j = int(p[4])
+                if j < 3:
+                    new = ["encoder", "block", str(i - 1), f"res_unit{j + 1}", unit[p[6]]] + p[7:]
+                else:
+                    new = ["encoder", "block", str(i - 1), "snake1" if j == 3 else "conv1"] + p[5:]
+        elif p[0] == "decoder" and p[1] == "model":
+            i = int(p[2])
+            if i == 0:
+                new = ["decoder", "conv1"] + p[3:]
+            elif i == 5:
+                new = ["decoder", "snake1"] + p[3:]
+            elif i == 6:
+                new = ["decoder", "conv2"] + p[3:]
+            else:  # DecoderBlock i-1: block.0 snake, block.1 transposed conv, block.{2,3,4} residual units
+                j = int(p[4])
+                if j < 2:
+                    new = ["decoder", "block", str(i - 1), "snake1" if j == 0 else "conv_t1"] + p[5:]
+                else:
+                    new = ["decoder", "block", str(i - 1), f"res_unit{j - 1}", unit[p[6]]] + p[7:]
+        else:
+            new = p
+        out[".".join(new)] = v
+    return out
+
+
 _ARCH = {  # descript-audio-codec 1.0.0 model zoo: tag -> (encoder rates, decoder rates, n_codebooks)
     "44khz": ((2, 4, 8, 8), (8, 8, 4, 2), 9),
     "24khz": ((2, 4, 5, 8), (8, 5, 4, 2), 32),
@@ -39,7 +86,7 @@ class DAC(Codec):
     max_chunk_samples = 64 * 441000  # ~0.2 KB of live activations per sample on the tensor path
 
     def _hop(self):
-        return 512
+        return math.prod(self._enc_rates)  # 512 (44.1 kHz) / 320 (16, 24 kHz)
 
     # single-plane weights for the k7 convolutions of the residual units (64 % of the FLOPs): decoder SI-SNR 47.0 -> 45.9 dB,
     # end-to-end code match 99.8 -> 99.4 %, step 329 -> 266 ms (scripts/weight_precision_probe.py; the transposed convs and
@@ -73,7 +120,7 @@ class DAC(Codec):
             except ImportError:
                 raise ImportError("`pip install descript-audio-codec` to use this module")
             state_dict = dac.DAC.load(str(dac.utils.download(model_type=tag))).state_dict()
-        self._build(state_dict)
+        self._build(descript_to_hf_keys(state_dict))
 
     def _w_split(self, name):
         # "exact": every encoder layer keeps the (hi, lo) weight pair (the tokens must be the reference's)
@@ -94,8 +141,8 @@ class DAC(Codec):
 
     def _convtr(self, sd, prefix, stride, snake):
         w = packing.fold_weight_norm(sd, prefix)  # [Cin, Cout, 2s]
-        if stride % 2:
-            raise NotImplementedError("odd-stride transposed convs (24/16 kHz DAC) are not on the fast path yet")
+        # padding ceil(s/2), no output_padding (descript 1.0.0, HF/dac:243-249): L s for an even stride, L s - 1 for the odd
+        # stride 5 of the 16 / 24 kHz models -- same 2-tap GEMM, one output row fewer
         spec = ConvSpec(packing.pack_convtr(w, stride), sd[prefix + ".bias"].float().repeat(stride), cout=w.shape[1],
                         geometry="tr", tr_stride=stride, tr_pad=math.ceil(stride / 2), act=ACT_SNAKE,
                         alpha=sd[snake + ".alpha"].float().reshape(-1).contiguous())
@@ -294,15 +341,16 @@ class DAC(Codec):
         for bi, (a_up, Wtr, s, units) in enumerate(self._tdec):
             p = math.ceil(s / 2)
             C = C // 2
-            Lout = L * s
+            Lout = L * s + s - 2 * p  # (L - 1) s - 2 p + 2 s: L s, or L s - 1 for an odd stride
             x = Act(B, Lout, C, dev, split=self._split_res(C))
             us = Act(B, Lout, C, dev, split=self._split(C))
             # transposed conv (k = 2s, stride s, padding p): 2-tap GEMM over n = (phase, cout), flat output shifted by p*C
             tc.conv_tc(Wtr, [Src(xs, taps=2, shift=-1)], L + 1, y=x, y_act=us, act=ACT_SNAKE, alpha=units[0][0].t, act_mod=C,
                        out_rows=Lout, out_ch=C, out_shift=p * C, name="convtr_tc")
             nxt = self._tdec[bi + 1][0] if bi + 1 < len(self._tdec) else self._tdec_last_alpha
-            # the last layer (k7, zero padding 3) reads 16-sample view rows: 3 zero rows in front, 13 behind
-            xs = self._tc_run_units(units, x, us, nxt, out_halo=(3, 13) if bi + 1 == len(self._tdec) else (0, 0))
+            # the last layer (k7, zero padding 3) reads 16-sample view rows: 3 zero rows in front, the rest of one more view
+            # row (13 for a length that is a multiple of 16) behind
+            xs = self._tc_run_units(units, x, us, nxt, out_halo=(3, tc.last_conv_right_halo(Lout, 3)) if bi + 1 == len(self._tdec) else (0, 0))
             L = Lout
         # last layer (Cout = 1, k7, zero padding 3, tanh) on the tap-GEMM kernel, 16 samples per GEMM row
         xs.fill_halo(PAD_ZERO)

@@ -15,7 +15,7 @@ class HostPipeline:
     def __init__(self, codec, fn=None, depth=2):
         """fn(codec, device_batch) -> device tensor (default: reconstruct = toks_to_sig(sig_to_toks(x)))."""
         self.codec = codec
-        self.fn = fn or (lambda c, x: c.toks_to_sig(c.sig_to_toks(x)))
+        self.fn = fn or (lambda c, x: c.reconstruct(x))
         self.depth = depth
         self.s_in = torch.cuda.Stream()
         self.s_out = torch.cuda.Stream()

@@ -283,13 +283,20 @@ def last_conv_weights_phased(spec, split=True):
     return TcWeights(w.reshape(P, -1), bias, split=split)
 
 
+def last_conv_right_halo(T, hl):
+    """right halo rows of the last layer's input: whole 16-sample view rows, one more than the output needs"""
+    return LAST_PHASES * (-(-T // LAST_PHASES) + 1) - hl - T
+
+
 def conv_last_phased(W: TcWeights, x_act: Act, *, tanh=False, name="conv_last_tc"):
-    """x_act [B, T, C] (activated) with hl = the layer's left padding rows and (hl + T + hr) a multiple of 16, halos filled
-    -> waveform [B, T] fp32 (T a multiple of 16)."""
+    """x_act [B, T, C] (activated) with hl = the layer's left padding rows and hr = last_conv_right_halo(T, hl), halos filled
+    -> waveform [B, T] fp32.  T need not be a multiple of 16 (DAC 16 / 24 kHz: 320 N - 8): the GEMM then computes the whole
+    last 16-sample row and the result is the [:, :T] view of it."""
     P = LAST_PHASES
     total = x_act.hl + x_act.L + x_act.hr
-    assert x_act.L % P == 0 and total % P == 0 and total // P >= x_act.L // P + 1
-    out = torch.empty((x_act.B, x_act.L), device=x_act.buf.device, dtype=torch.float32)
-    conv_tc(W, [Src(x_act, taps=2, origin=-x_act.hl, phases=P, rows=total // P)], x_act.L // P, y32=out.view(x_act.B, x_act.L // P, P),
+    rows = -(-x_act.L // P)
+    assert total % P == 0 and total // P >= rows + 1
+    out = torch.empty((x_act.B, rows * P), device=x_act.buf.device, dtype=torch.float32)
+    conv_tc(W, [Src(x_act, taps=2, origin=-x_act.hl, phases=P, rows=total // P)], rows, y32=out.view(x_act.B, rows, P),
             epi=ops.EPI_TANH if tanh else ops.EPI_NONE, name=name)
-    return out
+    return out if rows * P == x_act.L else out[:, :x_act.L]

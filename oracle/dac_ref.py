@@ -15,8 +15,15 @@ import torch.nn.functional as F
 
 from .resample_ref import resample
 
-ENC_RATIOS = (2, 4, 8, 8)
+ENC_RATIOS = (2, 4, 8, 8)  # 44 kHz model; the 16 / 24 kHz models use (2, 4, 5, 8) / (8, 5, 4, 2)
 DEC_RATIOS = (8, 8, 4, 2)
+
+
+def _strides(sd, side):
+    """strides of the four blocks, read off the state dict: every strided / transposed conv has kernel 2 * stride
+    (descript dac/model/dac.py EncoderBlock / DecoderBlock; HF/dac:210-262)."""
+    name = "encoder.block.{}.conv1.weight" if side == "enc" else "decoder.block.{}.conv_t1.weight"
+    return [sd[name.format(i)].shape[-1] // 2 for i in range(4)]
 
 
 def snake(x, alpha):
@@ -34,7 +41,7 @@ def res_unit(sd, p, x, dilation):
 def encoder(sd, x):
     """DacEncoder (HF/dac:442-472,210-231): [B,1,T] -> [B,1024,N]."""
     x = F.conv1d(x, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"], padding=3)
-    for i, s in enumerate(ENC_RATIOS):
+    for i, s in enumerate(_strides(sd, "enc")):
         p = f"encoder.block.{i}"
         for u, d in ((1, 1), (2, 3), (3, 9)):
             x = res_unit(sd, f"{p}.res_unit{u}", x, d)
@@ -43,9 +50,10 @@ def encoder(sd, x):
 
 
 def decoder(sd, z):
-    """DacDecoder (HF/dac:405-439,234-262): [B,1024,N] -> [B,1,512 N], tanh output."""
+    """DacDecoder (HF/dac:405-439,234-262): [B,1024,N] -> [B,1,512 N], tanh output.  An odd stride s (the 16 / 24 kHz models'
+    5: kernel 10, padding 3, no output_padding in descript 1.0.0 / the HF twin) gives (L - 1) s - 2 ceil(s/2) + 2 s = s L - 1."""
     x = F.conv1d(z, sd["decoder.conv1.weight"], sd["decoder.conv1.bias"], padding=3)
-    for i, s in enumerate(DEC_RATIOS):
+    for i, s in enumerate(_strides(sd, "dec")):
         p = f"decoder.block.{i}"
         x = F.conv_transpose1d(snake(x, sd[p + ".snake1.alpha"]), sd[p + ".conv_t1.weight"], sd[p + ".conv_t1.bias"], stride=s, padding=math.ceil(s / 2))
         for u, d in ((1, 1), (2, 3), (3, 9)):

@@ -182,10 +182,20 @@ DAC_ENC_RATIOS = (2, 4, 8, 8)  # descript-audio-codec 1.0.0 "44khz": encoder_rat
 DAC_DEC_RATIOS = (8, 8, 4, 2)
 
 
-def dac_state_dict(seed: int = 0, n_codebooks: int = 9):
-    """descript 44 kHz architecture in `transformers.DacModel` key format (HF/dac/modeling_dac.py:405-472,173-262):
-    encoder_hidden_size 64, decoder_hidden_size 1536, hidden 1024, 9 codebooks x 1024 x 8."""
-    g = _gen(seed + 202)
+DAC_ZOO = {  # descript-audio-codec 1.0.0 model zoo: tag -> (encoder rates, decoder rates, codebooks)
+    "44khz": ((2, 4, 8, 8), (8, 8, 4, 2), 9),
+    "24khz": ((2, 4, 5, 8), (8, 5, 4, 2), 32),
+    "16khz": ((2, 4, 5, 8), (8, 5, 4, 2), 12),
+}
+
+
+def dac_state_dict(seed: int = 0, n_codebooks: int = None, tag: str = "44khz"):
+    """descript architecture `tag` in `transformers.DacModel` key format (HF/dac/modeling_dac.py:405-472,173-262):
+    encoder_hidden_size 64, decoder_hidden_size 1536, hidden 1024, codebooks x 1024 x 8.  The 44 kHz dict is unchanged by the
+    `tag` argument (same generator seed and draw order); the 16 / 24 kHz models have an ODD stride (5) in both stacks."""
+    DAC_ENC_RATIOS, DAC_DEC_RATIOS, zoo_k = DAC_ZOO[tag]
+    n_codebooks = n_codebooks or zoo_k
+    g = _gen(seed + 202 + {"44khz": 0, "24khz": 1000, "16khz": 2000}[tag])
     sd = {}
 
     def snake(prefix, c):

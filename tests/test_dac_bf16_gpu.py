@@ -58,7 +58,7 @@ def test_dac_end_to_end_code_match_report(dac_sd, dev):
     assert toks.shape == ref.shape and toks.dtype == torch.int64
     per_stage = [(toks.cpu()[..., k] == ref[..., k]).float().mean().item() for k in range(9)]
     print("DAC bf16 end-to-end code match per stage:", [round(x, 4) for x in per_stage])
-    assert per_stage[0] > 0.8 and min(per_stage) > 0.4
+    assert per_stage[0] > 0.975 and min(per_stage) > 0.97  # measured: 0.994 .. 1.0 per stage (172 frames)
     rec = codec(sig.to(dev))
     assert tuple(rec.shape) == (2, 44032) and torch.isfinite(rec).all()
 

@@ -166,3 +166,59 @@ def test_autotune_skips_and_reports(monkeypatch):
     assert tc.autotune(("k", 2), vs) == "slow"                                   # no tuning: the first variant that launches
     with pytest.raises(RuntimeError, match="no variant"):
         tc.autotune(("k", 3), vs[:1] + vs[2:3])
+
+
+def _to_descript(sd):
+    """HF DacModel names -> descript-audio-codec 1.0.0 Sequential names with old-style weight_g / weight_v (test double of a
+    `dac.DAC.load(...).state_dict()`; the inverse of audiocodecs_b200.dac.descript_to_hf_keys)."""
+    import re
+    unit = {"snake1": "0", "conv1": "1", "snake2": "2", "conv2": "3"}
+    out = {}
+    for k, v in sd.items():
+        m = re.match(r"(encoder|decoder)\.block\.(\d)\.res_unit(\d)\.(\w+)\.(.+)", k)
+        if m:
+            side, i, u, part, rest = m.groups()
+            j = int(u) - 1 if side == "encoder" else int(u) + 1
+            top = f"encoder.block.{int(i) + 1}" if side == "encoder" else f"decoder.model.{int(i) + 1}"
+            name = f"{top}.block.{j}.block.{unit[part]}.{rest}"
+        else:
+            m = re.match(r"(encoder|decoder)\.block\.(\d)\.(snake1|conv1|conv_t1)\.(.+)", k)
+            if m:
+                side, i, part, rest = m.groups()
+                j = {"encoder": {"snake1": 3, "conv1": 4}, "decoder": {"snake1": 0, "conv_t1": 1}}[side][part]
+                top = f"encoder.block.{int(i) + 1}" if side == "encoder" else f"decoder.model.{int(i) + 1}"
+                name = f"{top}.block.{j}.{rest}"
+            else:
+                name = k
+                for a, b in (("encoder.conv1.", "encoder.block.0."), ("encoder.snake1.", "encoder.block.5."), ("encoder.conv2.", "encoder.block.6."),
+                             ("decoder.conv1.", "decoder.model.0."), ("decoder.snake1.", "decoder.model.5."), ("decoder.conv2.", "decoder.model.6.")):
+                    if k.startswith(a):
+                        name = b + k[len(a):]
+        if name.endswith(".weight") and "codebook" not in name:   # weight-normed in descript checkpoints: w = g v / |v|
+            g = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+            out[name + "_g"], out[name + "_v"] = g * 1.0, v * 3.0   # v deliberately not normalised
+        else:
+            out[name] = v
+    return out
+
+
+def test_dac_default_ctor_from_descript_checkpoint():
+    """`DAC(sample_rate)` -- orig_sample_rate=16000, the reference's default and its only downstream config --
+    builds from a descript-format state dict (Sequential key names, weight_g / weight_v, odd stride 5) and packs exactly what
+    the HF-format dict of the same weights packs."""
+    import audiocodecs_b200 as A
+    from audiocodecs_b200.dac import descript_to_hf_keys
+    from oracle import weights
+    sd = weights.dac_state_dict(0, tag="16khz")
+    dsd = _to_descript(sd)
+    assert "encoder.block.0.weight_g" in dsd and "decoder.model.1.block.1.weight_v" in dsd and "encoder.block.1.block.0.block.1.weight_g" in dsd
+    back = descript_to_hf_keys(dsd)
+    assert {k.replace(".weight_g", ".weight").replace(".weight_v", ".weight") for k in back} == set(sd)
+    a = A.DAC(16000, state_dict=dsd, precision="fp32")   # default orig_sample_rate=16000, num_codebooks=8
+    b = A.DAC(16000, 16000, num_codebooks=8, state_dict=sd, precision="fp32")
+    assert a.orig_sample_rate == 16000 and a.num_codebooks == 8 and a._dec_rates == (8, 5, 4, 2) and a._hop() == 320
+    for x, y in zip(a._specs, b._specs):
+        assert torch.allclose(x.w, y.w, atol=1e-6) and x.tr_stride == y.tr_stride
+    assert a._dec[1].out_len(10) == 80 and a._dec[5].tr_stride == 5 and a._dec[5].out_len(80) == 5 * 80 - 1   # stride 8: 8 L; stride 5: 5 L - 1
+    t = A.DAC(24000, 24000, num_codebooks=32, state_dict=weights.dac_state_dict(0, tag="24khz"))  # tensor path packs too
+    assert t.precision == "exact" and t._tdec[1][2] == 5

@@ -56,7 +56,7 @@ def test_mimi_end_to_end_code_match_report(mimi_sd, dev):
     assert toks.shape == ref.shape and toks.dtype == torch.int64
     per_stage = [(toks.cpu()[..., k] == ref[..., k]).float().mean().item() for k in range(8)]
     print("Mimi bf16 end-to-end code match per stage:", [round(x, 4) for x in per_stage])
-    assert per_stage[0] > 0.7 and min(per_stage) > 0.3
+    assert per_stage[0] > 0.95 and min(per_stage) > 0.93  # measured: 0.96 .. 1.0 per stage (50 frames: one frame = 2 points)
     rec = codec(sig.to(dev))
     assert tuple(rec.shape) == (2, 48000) and torch.isfinite(rec).all()
 

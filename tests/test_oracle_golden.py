@@ -80,3 +80,22 @@ def test_mimi_invalid_num_codebooks(mimi_sd):
     from oracle import mimi_ref
     with pytest.raises(ValueError):
         mimi_ref.rvq_encode(mimi_sd, torch.zeros(1, 512, 2), 33)
+
+
+@pytest.mark.parametrize("case", range(3))
+def test_dac_odd_stride_oracle_matches_reference_golden(case):
+    """the 16 / 24 kHz DAC architectures (stride-5 blocks; `DAC(sample_rate)`'s default): tests/golden/dac_odd_golden.pt was
+    recorded from the unmodified wrapper over the HF twin (oracle/make_golden_dac.py: golden_dac_odd)."""
+    import os
+    from oracle import dac_ref, weights
+    c = torch.load(os.path.join(weights.GOLDEN_DIR, "dac_odd_golden.pt"))["cases"][case]
+    sd = weights.dac_state_dict(0, tag=f"{c['orig_sample_rate'] // 1000}khz")
+    sig = make_input(c["seed"], c["B"], c["T"])
+    with torch.no_grad():
+        toks, gaps, _ = dac_ref.sig_to_toks(sd, sig, c["K"], c["sample_rate"], c["orig_sample_rate"], return_gaps=True)
+        rec = dac_ref.toks_to_sig(sd, c["toks"].long(), c["sample_rate"], c["orig_sample_rate"])
+    ref_toks = c["toks"].long()
+    assert toks.shape == ref_toks.shape
+    assert (toks == ref_toks)[gaps > 1e-4].all()
+    assert rec.shape == c["rec"].shape
+    assert (rec - c["rec"]).abs().max() <= 1e-4
