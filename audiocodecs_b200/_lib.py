@@ -45,7 +45,7 @@ class AcConvTcDesc(ctypes.Structure):
                 ("y_bstride", c_i64), ("y_act_bstride", c_i64), ("y32_bstride", c_i64), ("res_bstride", c_i64),
                 ("out_shift", c_i64), ("out_valid", c_i64),
                 ("batch", c_i32), ("m_rows", c_i32), ("n_tile_hint", c_i32), ("grid_hint", c_i32),
-                ("res_lo", c_vp), ("res32", c_vp), ("g_hint", c_i32)]
+                ("res_lo", c_vp), ("res32", c_vp), ("g_hint", c_i32), ("fmt", c_i32)]
 
 
 class AcResunitTcDesc(ctypes.Structure):
@@ -58,14 +58,14 @@ class AcResunitTcDesc(ctypes.Structure):
                 ("res", c_vp), ("res_lo", c_vp), ("res_bstride", c_i64),
                 ("y", c_vp), ("y_lo", c_vp), ("y_act", c_vp), ("y_act_lo", c_vp), ("y_bstride", c_i64), ("y_act_bstride", c_i64),
                 ("batch", c_i32), ("m_rows", c_i32), ("bk", c_i32), ("g_hint", c_i32), ("grid_hint", c_i32), ("dbl_hint", c_i32),
-                ("act0", c_i32), ("e_split", c_i32), ("x_from_a", c_i32), ("alpha0", c_vp), ("x_row_off", c_i32)]
+                ("act0", c_i32), ("e_split", c_i32), ("x_from_a", c_i32), ("alpha0", c_vp), ("x_row_off", c_i32), ("fmt", c_i32)]
 
 
 class AcLstmTcDesc(ctypes.Structure):
     """mirror of `struct ac_lstm_tc_desc`"""
     _fields_ = [("pre", c_vp), ("w_hh_bf16", c_vp), ("out_hi", c_vp), ("out_lo", c_vp), ("skip_hi", c_vp), ("skip_lo", c_vp),
                 ("final_hi", c_vp), ("final_lo", c_vp), ("skip_bstride", c_i64), ("final_bstride", c_i64),
-                ("final_act", c_i32), ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("dbg", c_vp), ("operand_fp16", c_i32)]
+                ("final_act", c_i32), ("batch", c_i32), ("steps", c_i32), ("hidden", c_i32), ("dbg", c_vp), ("operand_fp16", c_i32), ("out_fp16", c_i32), ("skip_fp16", c_i32)]
 
 
 def declared_symbols():
@@ -100,21 +100,21 @@ def lib():
         L.ac_layernorm_f32.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.c_float, c_vp]
         L.ac_attention_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp]
         L.ac_upsample_dw_f32.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]
-        L.ac_layernorm_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, ctypes.c_float, c_vp]
+        L.ac_layernorm_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, ctypes.c_float, c_i32, c_vp]
         L.ac_rope_table_f32.argtypes = [c_vp, c_vp, c_i32, c_i32, c_vp]
-        L.ac_attention_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_vp]
+        L.ac_attention_tc.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.c_float, c_i32, c_vp]
         L.ac_dac_rvq_encode_f32.argtypes = [c_vp] * 8 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_dac_rvq_encode_proj_f32.argtypes = [c_vp, c_i32] + [c_vp] * 6 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_dac_rvq_decode_f32.argtypes = [c_vp] * 5 + [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
         L.ac_conv_first_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32,
-                                         c_i32, c_i32, c_i32, c_i32, c_vp]
+                                         c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_conv_last_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]
         L.ac_lstm_tc.argtypes = [ctypes.POINTER(AcLstmTcDesc), c_vp]
-        L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]
+        L.ac_rvq_decode_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp]
         L.ac_conv_tc.argtypes = [ctypes.POINTER(AcConvTcDesc), c_vp]
         L.ac_resunit_tc.argtypes = [ctypes.POINTER(AcResunitTcDesc), c_vp]
-        L.ac_add_act_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp]
-        L.ac_f32_to_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_vp]
+        L.ac_add_act_bf16.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp]
+        L.ac_f32_to_split_bf16.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i64, c_i64, c_i64, c_i32, c_vp]
         L.ac_pad_halo_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
         _lib = L
     return _lib

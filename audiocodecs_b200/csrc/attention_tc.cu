@@ -36,6 +36,7 @@ struct AttnParams {
     float* out32;        // [B][T][H*D] or null
     __nv_bfloat16* out_hi;  // [B] x out_bs + [T][H*D], or null
     __nv_bfloat16* out_lo;
+    int out_f16;            // hi plane written as fp16 instead of bf16
     long long out_bs;
     int T, H, window;
     float qscale;        // 1/sqrt(D) * log2(e)
@@ -240,7 +241,7 @@ attention_tc_kernel(const AttnParams p) {
             for (int i = 0; i < 16; ++i) y[i] = o[c * 16 + i] * inv;
             if (p.out_hi) {
                 const size_t off = (size_t)b * p.out_bs + (size_t)qp * C + col + c * 16;
-                tcc::store_bf16x16(y, p.out_hi + off, p.out_lo ? p.out_lo + off : nullptr);
+                tcc::store_bf16x16(y, p.out_hi + off, p.out_lo ? p.out_lo + off : nullptr, p.out_f16 != 0);
             }
             if (p.out32) {
                 float4* dst = reinterpret_cast<float4*>(p.out32 + ((size_t)b * T + qp) * C + col + c * 16);
@@ -262,7 +263,7 @@ attention_tc_kernel(const AttnParams p) {
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                        __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, long long rows, int rows_per_clip, int C,
-                       long long out_bs, float eps) {
+                       long long out_bs, float eps, int out_f16) {
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -294,12 +295,11 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ w,
             const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
             const float y0 = (v[k].x - mean) * rstd * ww.x + bb.x, y1 = (v[k].y - mean) * rstd * ww.y + bb.y;
             const float y2 = (v[k].z - mean) * rstd * ww.z + bb.z, y3 = (v[k].w - mean) * rstd * ww.w + bb.w;
-            const uint32_t h0 = tcc::pack_bf16(y0, y1), h1 = tcc::pack_bf16(y2, y3);
+            const uint32_t h0 = tcc::pack16(y0, y1, out_f16 != 0), h1 = tcc::pack16(y2, y3, out_f16 != 0);
             *reinterpret_cast<uint2*>(o_hi + off + c) = make_uint2(h0, h1);
             if (o_lo) {
-                const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&h0), a1 = *reinterpret_cast<const __nv_bfloat162*>(&h1);
-                *reinterpret_cast<uint2*>(o_lo + off + c) = make_uint2(tcc::pack_bf16(y0 - __low2float(a0), y1 - __high2float(a0)),
-                                                                       tcc::pack_bf16(y2 - __low2float(a1), y3 - __high2float(a1)));
+                const float2 a0 = tcc::unpack16(h0, out_f16 != 0), a1 = tcc::unpack16(h1, out_f16 != 0);
+                *reinterpret_cast<uint2*>(o_lo + off + c) = make_uint2(tcc::pack_bf16(y0 - a0.x, y1 - a0.y), tcc::pack_bf16(y2 - a1.x, y3 - a1.y));
             }
         }
 }
@@ -317,12 +317,12 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __r
 }  // namespace
 
 extern "C" int ac_layernorm_split_bf16(const float* x, const float* w, const float* b, void* out_hi, void* out_lo, int32_t batch,
-                                       int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, void* stream) {
+                                       int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, int32_t out_f16, void* stream) {
     AC_REQUIRE(x && w && b && out_hi && batch > 0 && rows_per_clip > 0, "ac_layernorm_split_bf16: bad arguments");
     AC_REQUIRE(C > 0 && C <= 1024 && C % 128 == 0 && out_bstride % 4 == 0, "ac_layernorm_split_bf16: C %d (multiple of 128, <= 1024)", C);
     const long long rows = (long long)batch * rows_per_clip;
     layernorm_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        x, w, b, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, rows, rows_per_clip, C, out_bstride, eps);
+        x, w, b, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, rows, rows_per_clip, C, out_bstride, eps, out_f16);
     return ac::finish_launch("ac_layernorm_split_bf16");
 }
 
@@ -333,7 +333,8 @@ extern "C" int ac_rope_table_f32(const float* inv_freq, float* table, int32_t T,
 }
 
 extern "C" int ac_attention_tc(const float* qkv, const float* rope, float* out32, void* out_hi, void* out_lo, int64_t out_bstride,
-                               int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, void* stream) {
+                               int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, int32_t out_f16,
+                               void* stream) {
     AC_REQUIRE(qkv && rope && (out32 || out_hi), "ac_attention_tc: null pointer");
     AC_REQUIRE(out_hi || !out_lo, "ac_attention_tc: lo plane without hi plane");
     AC_REQUIRE(head_dim == D, "ac_attention_tc: head_dim %d (built for %d)", head_dim, D);
@@ -348,7 +349,7 @@ extern "C" int ac_attention_tc(const float* qkv, const float* rope, float* out32
     }
     AttnParams p{};
     p.qkv = qkv; p.rope = rope; p.out32 = out32;
-    p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo; p.out_bs = out_bstride;
+    p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo; p.out_bs = out_bstride; p.out_f16 = out_f16 ? 1 : 0;
     p.T = T; p.H = heads; p.window = window;
     p.qscale = scaling * 1.4426950408889634f;
     dim3 grid((T + QT - 1) / QT, heads, batch);

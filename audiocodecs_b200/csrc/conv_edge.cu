@@ -5,6 +5,7 @@
 // Both keep the reference's padding rule (reflect with the tiny-input zero extension / zero) by index arithmetic on
 // a shared-memory tile, so no padded copy of the 10 s x 64-clip tensors is ever made.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -38,20 +39,29 @@ struct FirstP {
     __nv_bfloat16* y_lo; __nv_bfloat16* y_act_lo;   // optional lo planes: bf16(v - float(bf16(v)))
     long long y_bs, ya_bs;
     int T, K, pad_left, pad_mode, reflect_len, act;
+    int out_f16;   // hi planes are written as IEEE fp16 (saturating) instead of bf16; lo planes stay bf16
 };
 
-// 8 values -> the 16 bytes of their bf16 roundings; with `lo` also the 16 bytes of the rounding residuals
-__device__ __forceinline__ void store8_split(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
+// 8 values -> the 16 bytes of their 16-bit roundings; with `lo` also the 16 bytes of the rounding residuals (bf16)
+__device__ __forceinline__ void store8_split(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo, bool f16) {
     uint32_t q[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = pack2(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) q[i] = f16 ? pack2_f16(v[2 * i], v[2 * i + 1]) : pack2(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(hi) = make_uint4(q[0], q[1], q[2], q[3]);
     if (lo) {
         uint32_t r[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&q[i]);
-            r[i] = pack2(v[2 * i] - __low2float(h2), v[2 * i + 1] - __high2float(h2));
+            float2 f;
+            if (f16) f = __half22float2(*reinterpret_cast<const __half2*>(&q[i]));
+            else { const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&q[i]); f = make_float2(__low2float(h2), __high2float(h2)); }
+            r[i] = pack2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
         }
         *reinterpret_cast<uint4*>(lo) = make_uint4(r[0], r[1], r[2], r[3]);
     }
@@ -105,14 +115,14 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
             }
         }
         const long long off = (long long)t * C + grp * 8;
-        if (p.y) store8_split(acc, p.y + (long long)b * p.y_bs + off, p.y_lo ? p.y_lo + (long long)b * p.y_bs + off : nullptr);
+        if (p.y) store8_split(acc, p.y + (long long)b * p.y_bs + off, p.y_lo ? p.y_lo + (long long)b * p.y_bs + off : nullptr, p.out_f16 != 0);
         if (p.y_act) {
             float a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 a[c] = ACT == AC_ACT_ELU ? (acc[c] > 0.f ? acc[c] : exp2f(acc[c] * 1.4426950408889634f) - 1.0f)
                                          : (ACT == AC_ACT_SNAKE ? snake_fast(acc[c], al[c], ral[c]) : acc[c]);
-            store8_split(a, p.y_act + (long long)b * p.ya_bs + off, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + off : nullptr);
+            store8_split(a, p.y_act + (long long)b * p.ya_bs + off, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + off : nullptr, p.out_f16 != 0);
         }
     }
 }
@@ -166,14 +176,14 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const LastP p) {
 extern "C" int ac_conv_first_bf16(const float* x, const float* w, const float* bias, const float* alpha, const int32_t* vlen,
                                   void* y, void* y_act, void* y_lo, void* y_act_lo, int64_t y_bstride, int64_t y_act_bstride,
                                   int32_t batch, int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode,
-                                  int32_t reflect_len, int32_t act, void* stream) {
+                                  int32_t reflect_len, int32_t act, int32_t out_f16, void* stream) {
     AC_REQUIRE(x && w && (y || y_act), "ac_conv_first_bf16: null pointer");
     AC_REQUIRE(batch > 0 && batch <= 65535 && T > 0 && K >= 1 && K <= MAXK, "ac_conv_first_bf16: bad sizes");
     AC_REQUIRE(act != AC_ACT_SNAKE || alpha, "ac_conv_first_bf16: snake needs alpha");
     AC_REQUIRE((!y_lo || y) && (!y_act_lo || y_act), "ac_conv_first_bf16: lo plane without its hi plane");
     FirstP p{x, w, bias, alpha, vlen, (__nv_bfloat16*)y, (__nv_bfloat16*)y_act, (__nv_bfloat16*)y_lo, (__nv_bfloat16*)y_act_lo,
              y_bstride, y_act_bstride,
-             T, K, pad_left, pad_mode, reflect_len < T ? T : reflect_len, act};
+             T, K, pad_left, pad_mode, reflect_len < T ? T : reflect_len, act, out_f16 ? 1 : 0};
     dim3 grid((T + 2047) / 2048, batch);
     cudaStream_t s = (cudaStream_t)stream;
 #define AC_FIRST(CC)                                                                                     \

@@ -63,9 +63,12 @@ struct TcParams {
     int n_total, n_tile, n_tiles, m_rows, m_groups, batch, G;
     int a_stages, w_stages, acc_stages;
     int w_resident, w_split;
+    int f16;       // hi planes of the A sources and the W_hi / W_lo planes are fp16 (else bf16); lo planes of A are always bf16
+    int w_hib;     // f16 only: an extra bf16(W) plane (after W_hi [W_lo]) that the A_lo products multiply
+    int y_f16, ya_f16, res_f16;   // hi-plane formats of the outputs / the residual
     uint32_t a_stage_bytes, a_plane_bytes;  // lo block sits a_plane_bytes after the hi block
-    uint32_t w_stage_bytes, w_plane_bytes;  // streaming ring: W_lo sits w_plane_bytes after W_hi
-    uint32_t w_kb_bytes, w_res_plane;       // resident: block kb at kb*w_kb_bytes, lo plane w_res_plane further
+    uint32_t w_stage_bytes, w_plane_bytes;  // streaming ring: plane q (W_hi, [W_lo], [bf16 W_hi]) sits q * w_plane_bytes after W_hi
+    uint32_t w_kb_bytes, w_res_plane;       // resident: block kb at kb*w_kb_bytes, plane q at q * w_res_plane
     uint32_t tmem_cols;
     const float* bias;
     const float* alpha;
@@ -167,7 +170,7 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                     for (int i = 0; i < 16; ++i) o[i] = tanhf(o[i]);
                 }
                 if (has_res) {
-                    add_bf16x16(o, rcur[0], rcur[1]);
+                    add_bf16x16(o, rcur[0], rcur[1], p.res_f16 != 0);
                     if (has_res_lo) add_bf16x16(o, rcur[2], rcur[3]);
                 }
                 if (has_res32) {
@@ -184,7 +187,7 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                     st_global_256(d + 8, __float_as_uint(o[8]), __float_as_uint(o[9]), __float_as_uint(o[10]), __float_as_uint(o[11]),
                                   __float_as_uint(o[12]), __float_as_uint(o[13]), __float_as_uint(o[14]), __float_as_uint(o[15]));
                 }
-                if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr);
+                if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr, p.y_f16 != 0);
                 if (p.y_act) {
                     if (ACT == AC_ACT_ELU) {
 #pragma unroll
@@ -207,7 +210,7 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                             }
                         }
                     }
-                    store_bf16x16(o, p.y_act + (long long)b * p.ya_bs + flat, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + flat : nullptr);
+                    store_bf16x16(o, p.y_act + (long long)b * p.ya_bs + flat, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + flat : nullptr, p.ya_f16 != 0);
                 }
                 continue;
             }
@@ -234,7 +237,7 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                     for (int i = 0; i < 8; ++i) o[i] = tanhf(o[i]);
                 }
                 if (has_res) {
-                    add_bf16x8(o, p.res + (long long)b * p.res_bs + f);
+                    add_bf16x8(o, p.res + (long long)b * p.res_bs + f, p.res_f16 != 0);
                     if (has_res_lo) add_bf16x8(o, p.res_lo + (long long)b * p.res_bs + f);
                 }
                 if (has_res32) {
@@ -249,9 +252,9 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
                     d[1] = make_float4(o[4], o[5], o[6], o[7]);
                 }
                 if (p.y) {
-                    const uint4 q = pack8(o);
+                    const uint4 q = pack8(o, p.y_f16 != 0);
                     *reinterpret_cast<uint4*>(p.y + (long long)b * p.y_bs + f) = q;
-                    if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + (long long)b * p.y_bs + f) = pack_lo(o, q);
+                    if (p.y_lo) *reinterpret_cast<uint4*>(p.y_lo + (long long)b * p.y_bs + f) = pack_lo(o, q, p.y_f16 != 0);
                 }
                 if (p.y_act) {
                     float a[8];
@@ -275,9 +278,9 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a[i] = o[i];
                     }
-                    const uint4 q = pack8(a);
+                    const uint4 q = pack8(a, p.ya_f16 != 0);
                     *reinterpret_cast<uint4*>(p.y_act + (long long)b * p.ya_bs + f) = q;
-                    if (p.y_act_lo) *reinterpret_cast<uint4*>(p.y_act_lo + (long long)b * p.ya_bs + f) = pack_lo(a, q);
+                    if (p.y_act_lo) *reinterpret_cast<uint4*>(p.y_act_lo + (long long)b * p.ya_bs + f) = pack_lo(a, q, p.ya_f16 != 0);
                 }
             }
         }
@@ -298,7 +301,9 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uin
     const bool leader = elect_one();
     int astage = 0, wstage = 0;
     uint32_t aphase = 0, wphase = 0;
-    const uint32_t idesc = make_idesc_bf16(TILE_M, p.n_tile);
+    const uint32_t idesc = p.f16 ? make_idesc_f16(TILE_M, p.n_tile) : make_idesc_bf16(TILE_M, p.n_tile);  // hi-plane products
+    const uint32_t idesc_lo = make_idesc_bf16(TILE_M, p.n_tile);  // A_lo (always bf16) x bf16(W_hi)
+    const uint32_t hib_plane = p.w_hib ? (uint32_t)(1 + p.w_split) : 0u;  // which W plane the A_lo product reads
     const uint32_t row_bytes = KSTEPS * 32;
     const uint64_t desc_base = make_smem_desc(0, row_bytes);  // everything but the start address
     const uint32_t a_ring_u = smem_u32(a_ring), w_area_u = smem_u32(w_area);
@@ -320,18 +325,21 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uin
                 tc_fence_after();
                 const uint32_t a_hi = a_ring_u + astage * p.a_stage_bytes;
                 for (int j = 0; j < taps; ++j) {
-                    uint32_t w_hi, w_lo;
+                    uint32_t w_hi, w_lo, w_hib;
                     if (p.w_resident) {
                         w_hi = w_area_u + (S.kb0 + j * chunks + cc) * p.w_kb_bytes;
                         w_lo = w_hi + p.w_res_plane;
+                        w_hib = w_hi + hib_plane * p.w_res_plane;
                     } else {
                         mbar_wait(&w_full[wstage], wphase);
                         tc_fence_after();
                         w_hi = w_area_u + wstage * p.w_stage_bytes;
                         w_lo = w_hi + p.w_plane_bytes;
+                        w_hib = w_hi + hib_plane * p.w_plane_bytes;
                     }
                     const uint64_t bdesc_hi = desc_base | ((w_hi & 0x3FFFFu) >> 4);
                     const uint64_t bdesc_lo = desc_base | ((w_lo & 0x3FFFFu) >> 4);
+                    const uint64_t bdesc_hib = desc_base | ((w_hib & 0x3FFFFu) >> 4);
                     uint32_t a_addr = a_hi + j * dil_bytes;
                     uint32_t d_tmem = d_base;
                     for (int g = 0; g < p.G; ++g, a_addr += TILE_M * row_bytes, d_tmem += p.n_tile) {
@@ -343,10 +351,10 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uin
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1u);
                             }
-                            if (has_lo) {  // split activations: A_lo * W_hi (A_lo * W_lo is below fp32 noise)
+                            if (has_lo) {  // split activations: A_lo * W_hi (A_lo * W_lo is below fp32 noise); bf16 x bf16
                                 const uint64_t adesc_lo = desc_base | (((a_addr + p.a_plane_bytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc_lo + 2 * k, bdesc_hi + 2 * k, idesc, 1u);
+                                for (int k = 0; k < KSTEPS; ++k) umma_bf16(d_tmem, adesc_lo + 2 * k, bdesc_hib + 2 * k, idesc_lo, 1u);
                             }
                         }
                     }
@@ -372,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* w_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
-    const size_t w_area_bytes = p.w_resident ? (size_t)p.w_res_plane * (1 + p.w_split) : (size_t)p.w_stages * p.w_stage_bytes;
+    const size_t w_area_bytes = p.w_resident ? (size_t)p.w_res_plane * (1 + p.w_split + p.w_hib) : (size_t)p.w_stages * p.w_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_area + w_area_bytes);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + MAX_A_STAGES;
@@ -453,11 +461,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             const uint32_t blk_bytes = p.n_tile * row_bytes;
             if (p.w_resident) {
                 // whole matrix once: block kb = [n_total x bk] at kb * w_kb_bytes, lo plane after all hi blocks
-                mbar_arrive_expect_tx(wres_bar, (uint32_t)p.num_kb * blk_bytes * (1 + p.w_split));
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    tma_load_2d(w_area + (size_t)kb * p.w_kb_bytes, &maps.w, wres_bar, kb * p.bk, 0);
-                    if (p.w_split) tma_load_2d(w_area + p.w_res_plane + (size_t)kb * p.w_kb_bytes, &maps.w, wres_bar, kb * p.bk, p.w_rows);
-                }
+                const int planes = 1 + p.w_split + p.w_hib;
+                mbar_arrive_expect_tx(wres_bar, (uint32_t)p.num_kb * blk_bytes * planes);
+                for (int kb = 0; kb < p.num_kb; ++kb)
+                    for (int q = 0; q < planes; ++q)
+                        tma_load_2d(w_area + (size_t)q * p.w_res_plane + (size_t)kb * p.w_kb_bytes, &maps.w, wres_bar, kb * p.bk, q * p.w_rows);
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
@@ -469,10 +477,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                             for (int j = 0; j < S.taps; ++j) {
                                 const int kb = S.kb0 + j * S.chunks + cc;
                                 mbar_wait(&w_empty[stage], phase ^ 1);
-                                mbar_arrive_expect_tx(&w_full[stage], blk_bytes * (1 + p.w_split));
+                                const int planes = 1 + p.w_split + p.w_hib;
+                                mbar_arrive_expect_tx(&w_full[stage], blk_bytes * planes);
                                 uint8_t* dst = w_area + (size_t)stage * p.w_stage_bytes;
-                                tma_load_2d(dst, &maps.w, &w_full[stage], kb * p.bk, nt * p.n_tile);
-                                if (p.w_split) tma_load_2d(dst + p.w_plane_bytes, &maps.w, &w_full[stage], kb * p.bk, p.w_rows + nt * p.n_tile);
+                                for (int q = 0; q < planes; ++q)
+                                    tma_load_2d(dst + (size_t)q * p.w_plane_bytes, &maps.w, &w_full[stage], kb * p.bk, q * p.w_rows + nt * p.n_tile);
                                 if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -547,10 +556,13 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     }
 
     const int w_split = d->w_split ? 1 : 0;
+    const int f16 = (d->fmt & AC_FMT_A_F16) ? 1 : 0, w_hib = (d->fmt & AC_FMT_W_HIB) ? 1 : 0;
+    AC_REQUIRE(!w_hib || f16, "ac_conv_tc: the extra bf16(W) plane only exists for fp16 operands");
+    const int w_planes = 1 + w_split + w_hib;
     // N tile: the largest of {256,...,16} that does not over-pad; split weights hold two W tiles per stage -> cap at 128
     int n_tile = 16;
     for (int c : {256, 192, 128, 96, 64, 48, 32, 16})
-        if ((!w_split || c <= 128) && d->n_total % c == 0) { n_tile = c; break; }
+        if ((w_planes == 1 || c <= 128) && d->n_total % c == 0) { n_tile = c; break; }
     if (d->n_total % n_tile != 0) n_tile = d->n_total >= 128 ? 128 : 16;
     if (d->n_tile_hint > 0) n_tile = d->n_tile_hint;
     AC_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "ac_conv_tc: n_tile %d", n_tile);
@@ -566,6 +578,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
         if (halo > max_halo) max_halo = halo;
     }
     AC_REQUIRE(k_total == d->k_total, "ac_conv_tc: k_total %d != sum of taps*channels %d", d->k_total, k_total);
+    AC_REQUIRE(!(f16 && any_lo) || w_hib, "ac_conv_tc: fp16 operands with a lo plane need the extra bf16(W) plane (AC_FMT_W_HIB)");
     AC_REQUIRE(((uintptr_t)d->w & 15) == 0 && (k_total * 2) % 16 == 0, "ac_conv_tc: weights not 16-byte aligned");
 
     const int act_mod = d->act_mod > 0 ? d->act_mod : d->n_total;
@@ -589,7 +602,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
             if (!ok) continue;
             const int num_kb = k_total / bk;
             const uint32_t w_kb_bytes = round_up((uint32_t)d->n_total * bk * 2, 1024);
-            const size_t w_res_total = (size_t)num_kb * w_kb_bytes * (1 + w_split);
+            const size_t w_res_total = (size_t)num_kb * w_kb_bytes * w_planes;
             const bool resident = n_tiles == 1 && n_tile == d->n_total && w_res_total <= 96 * 1024;
             for (int G : {4, 2, 1}) {
                 if (g_only > 0 && G != g_only) continue;
@@ -609,7 +622,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
                 }
                 const uint32_t a_stage = a_plane * (any_lo ? 2 : 1);
                 const uint32_t w_plane = round_up((uint32_t)n_tile * bk * 2, 1024);
-                const uint32_t w_stage = w_plane * (1 + w_split);
+                const uint32_t w_stage = w_plane * w_planes;
                 const size_t budget = SMEM_LIMIT - fixed;
                 int a_stages, w_stages;
                 if (resident) {
@@ -651,7 +664,8 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     }
     AC_REQUIRE(found, "ac_conv_tc: no tiling fits shared memory (n_total %d k_total %d)", d->n_total, k_total);
     const int bk = p.bk;
-    p.w_split = w_split;
+    p.w_split = w_split; p.f16 = f16; p.w_hib = w_hib;
+    p.y_f16 = (d->fmt & AC_FMT_Y_F16) ? 1 : 0; p.ya_f16 = (d->fmt & AC_FMT_YACT_F16) ? 1 : 0; p.res_f16 = (d->fmt & AC_FMT_RES_F16) ? 1 : 0;
     p.acc_stages = 2 * p.G * n_tile <= 512 ? 2 : 1;
     uint32_t cols = 32;
     while (cols < (uint32_t)(p.acc_stages * p.G * n_tile)) cols <<= 1;
@@ -687,7 +701,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     }
     for (int s = n_ms; s < MAX_SRC; ++s) { maps.a[s] = maps.a[0]; maps.a_lo[s] = maps.a[0]; }
     {
-        cuuint64_t gdim[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_total * (1 + w_split)};  // W_lo stacked under W_hi
+        cuuint64_t gdim[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_total * w_planes};  // W_lo / bf16(W) stacked under W_hi
         cuuint64_t gstr[1] = {(cuuint64_t)k_total * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)n_tile};
         cuuint32_t est[2] = {1, 1};
@@ -720,7 +734,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
                     al(d->res, 32) && al(d->res_lo, 32) && al(d->res32, 32);
     }
 
-    const size_t w_area = p.w_resident ? (size_t)p.w_res_plane * (1 + w_split) : (size_t)p.w_stages * p.w_stage_bytes;
+    const size_t w_area = p.w_resident ? (size_t)p.w_res_plane * w_planes : (size_t)p.w_stages * p.w_stage_bytes;
     const size_t smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + w_area;
     AC_REQUIRE(smem <= (size_t)SMEM_LIMIT, "ac_conv_tc: shared memory %zu", smem);
     static bool attr_set = false;

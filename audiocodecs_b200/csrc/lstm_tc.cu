@@ -53,6 +53,7 @@ struct LstmTcParams {
     long long skip_bs, fin_bs;
     int fin_act, batch, steps;
     int f16;    // operands (W_hh in tensor memory, h in shared memory) are fp16 instead of bf16
+    int out_f16, skip_f16;  // hi-plane formats of out / final and of skip (lo planes are bf16)
     long long* dbg;  // optional [steps][8] clock64 samples from cluster 0 / CTA 0 (profiling aid)
 };
 
@@ -86,6 +87,17 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return copysignf(t, x);
 }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// one hi-plane element (bf16, or fp16 saturating at +-65504); returns the stored value
+__device__ __forceinline__ float store_hi(__nv_bfloat16* dst, float v, bool f16) {
+    if (f16) {
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        *reinterpret_cast<__half*>(dst) = h;
+        return __half2float(h);
+    }
+    const __nv_bfloat16 b = __float2bfloat16(v);
+    *dst = b;
+    return __bfloat162float(b);
+}
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -171,7 +183,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         // issues the 32 tcgen05.mma of the step back to back
         const bool leader = elect_one();
         // kind::f16 instruction descriptor: operand format bits 7-9 (A) / 10-12 (B) = 1 for bf16, 0 for fp16
-        const uint32_t idesc = p.f16 ? (make_idesc_bf16(128, NB) & ~((7u << 7) | (7u << 10))) : make_idesc_bf16(128, NB);
+        const uint32_t idesc = p.f16 ? make_idesc_f16(128, NB) : make_idesc_bf16(128, NB);
         uint64_t desc_base = 0;
         desc_base |= (uint64_t)((B_KSTR >> 4) & 0x3FFF) << 16;  // leading byte offset = K-direction core-matrix stride
         desc_base |= (uint64_t)((B_NSTR >> 4) & 0x3FFF) << 32;  // stride byte offset = 8-row group stride
@@ -223,22 +235,20 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
                 const int clip = clip0 + ew * CPT + i;
                 if (clip >= p.batch) continue;
                 const float h = h_prev[i];
-                const __nv_bfloat16 hb = __float2bfloat16(h);
                 const size_t o = ((size_t)clip * p.steps + t) * HID + gu;
                 if (p.out_hi) {
-                    p.out_hi[o] = hb;
-                    if (p.out_lo) p.out_lo[o] = __float2bfloat16(h - __bfloat162float(hb));
+                    const float hv = store_hi(p.out_hi + o, h, p.out_f16 != 0);
+                    if (p.out_lo) p.out_lo[o] = __float2bfloat16(h - hv);
                 }
                 if (p.fin_hi) {
                     float y = h;
                     const size_t so = (size_t)clip * p.skip_bs + (size_t)t * HID + gu;
-                    if (p.skip_hi) y += __bfloat162float(p.skip_hi[so]);
+                    if (p.skip_hi) y += p.skip_f16 ? __half2float(reinterpret_cast<const __half*>(p.skip_hi)[so]) : __bfloat162float(p.skip_hi[so]);
                     if (p.skip_lo) y += __bfloat162float(p.skip_lo[so]);
                     if (p.fin_act == AC_ACT_ELU) y = elu_f(y);
-                    const __nv_bfloat16 yb = __float2bfloat16(y);
                     const size_t fo = (size_t)clip * p.fin_bs + (size_t)t * HID + gu;
-                    p.fin_hi[fo] = yb;
-                    if (p.fin_lo) p.fin_lo[fo] = __float2bfloat16(y - __bfloat162float(yb));
+                    const float yv = store_hi(p.fin_hi + fo, y, p.out_f16 != 0);
+                    if (p.fin_lo) p.fin_lo[fo] = __float2bfloat16(y - yv);
                 }
             }
         };
@@ -338,6 +348,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     p.fin_act = d->final_act; p.batch = d->batch; p.steps = d->steps;
     p.dbg = (long long*)d->dbg;
     p.f16 = d->operand_fp16 ? 1 : 0;
+    p.out_f16 = d->out_fp16 ? 1 : 0; p.skip_f16 = d->skip_fp16 ? 1 : 0;
 
     const int clusters = (d->batch + nbv - 1) / nbv;
     cudaLaunchConfig_t cfg{};

@@ -60,6 +60,7 @@ struct RuParams {
     int raw, act0, e_split, x_from_a, sc_row_off;
     uint32_t e_stage_bytes, e_plane_bytes;
     const float* alpha0;
+    int f16, w1_hib, w2_hib, y_f16, ya_f16, res_f16;  // formats (AC_FMT_*): hi planes fp16 / extra bf16(W) planes for the lo products
     int dbl;                      // acc1 and the hidden tile are double-buffered: GEMM1 / epilogue 1 of tile i+1 overlap GEMM2 / epilogue 2 of tile i
     uint32_t h_stage_bytes;       // one hidden-tile buffer (all k-blocks, hi [+lo] planes)
     const float *bias1, *alpha1, *bias2, *alpha2;
@@ -77,11 +78,12 @@ __device__ __forceinline__ void load_block(const CUtensorMap* map, uint8_t* dst,
 // one W block against the G sub-tiles of one A block (rows of KS*32 bytes); `a_lo_off` != 0 adds the A_lo * W_hi product
 template <int KS>
 __device__ __forceinline__ void issue_blocks(bool leader, int G, uint32_t d0, uint32_t dstep, uint32_t a_addr, uint32_t a_lo_off,
-                                             uint32_t w_hi, uint32_t w_lo, bool wsplit, uint32_t idesc, uint32_t acc) {
+                                             uint32_t w_hi, uint32_t w_lo, bool wsplit, uint32_t idesc, uint32_t acc, uint32_t w_hib,
+                                             uint32_t idesc_lo) {
     constexpr uint32_t row_bytes = KS * 32;
     const uint64_t desc_base = make_smem_desc(0, row_bytes);
     auto desc = [&](uint32_t addr) { return desc_base | ((addr & 0x3FFFFu) >> 4); };
-    const uint64_t bh = desc(w_hi), bl = desc(w_lo);
+    const uint64_t bh = desc(w_hi), bl = desc(w_lo), bhb = desc(w_hib);
     for (int g = 0; g < G; ++g, a_addr += TILE_M * row_bytes, d0 += dstep) {
         const uint64_t ad = desc(a_addr);
         if (leader) {
@@ -92,9 +94,9 @@ __device__ __forceinline__ void issue_blocks(bool leader, int G, uint32_t d0, ui
                 for (int k = 0; k < KS; ++k) umma_bf16(d0, ad + 2 * k, bl + 2 * k, idesc, 1u);
             }
             if (a_lo_off) {
-                const uint64_t al = desc(a_addr + a_lo_off);
+                const uint64_t al = desc(a_addr + a_lo_off);  // A_lo (bf16) x bf16(W_hi)
 #pragma unroll
-                for (int k = 0; k < KS; ++k) umma_bf16(d0, al + 2 * k, bh + 2 * k, idesc, 1u);
+                for (int k = 0; k < KS; ++k) umma_bf16(d0, al + 2 * k, bhb + 2 * k, idesc_lo, 1u);
             }
         }
     }
@@ -108,23 +110,29 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
     const bool leader = elect_one();
     int astage = 0, wstage = 0;
     uint32_t aphase = 0, wphase = 0;
-    const uint32_t idesc1 = make_idesc_bf16(TILE_M, p.ch), idesc2 = make_idesc_bf16(TILE_M, p.cout);
+    const uint32_t idesc1 = p.f16 ? make_idesc_f16(TILE_M, p.ch) : make_idesc_bf16(TILE_M, p.ch);
+    const uint32_t idesc2 = p.f16 ? make_idesc_f16(TILE_M, p.cout) : make_idesc_bf16(TILE_M, p.cout);
+    const uint32_t idesc1_lo = make_idesc_bf16(TILE_M, p.ch), idesc2_lo = make_idesc_bf16(TILE_M, p.cout);
+    // which plane (0 = W_hi, 1 = W_lo, 2 = bf16 W_hi) the A_lo products read
+    const uint32_t hib1 = p.w1_hib ? (uint32_t)(1 + p.w1_split) : 0u, hib2 = p.w2_hib ? (uint32_t)(1 + p.w2_split) : 0u;
     constexpr uint32_t row_bytes = KA * 32;
     const uint32_t a_ring_u = smem_u32(a_ring), e_ring_u = smem_u32(e_ring), w_area_u = smem_u32(w_area), h_u = smem_u32(h_tile);
     const uint32_t acc2 = tmem_base + p.acc2_col;
     int a_base[2] = {0, 0};  // ring stage of chunk 0 of the tiles in flight (raw rows are read again by GEMM2's shortcut)
     if (p.w_resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
     // next W block: resident address or ring slot (returns hi address; lo = hi + plane).  which: 0 = W1, 1 = W2 hidden part, 2 = W2 x part
-    auto w_get = [&](int which, int kb, uint32_t& w_hi, uint32_t& w_lo) {
+    auto w_get = [&](int which, int kb, uint32_t& w_hi, uint32_t& w_lo, uint32_t& w_hib) {
+        const uint32_t hq = which == 0 ? hib1 : hib2;
         if (p.w_resident) {
-            if (which == 0) { w_hi = w_area_u + kb * p.w1_kb_bytes; w_lo = w_hi + p.w1_res_plane; }
-            else if (which == 1) { w_hi = w_area_u + p.w2h_res_off + kb * p.w2h_kb_bytes; w_lo = w_hi + p.w2h_res_plane; }
-            else { w_hi = w_area_u + p.w2x_res_off + kb * p.w2x_kb_bytes; w_lo = w_hi + p.w2x_res_plane; }
+            if (which == 0) { w_hi = w_area_u + kb * p.w1_kb_bytes; w_lo = w_hi + p.w1_res_plane; w_hib = w_hi + hq * p.w1_res_plane; }
+            else if (which == 1) { w_hi = w_area_u + p.w2h_res_off + kb * p.w2h_kb_bytes; w_lo = w_hi + p.w2h_res_plane; w_hib = w_hi + hq * p.w2h_res_plane; }
+            else { w_hi = w_area_u + p.w2x_res_off + kb * p.w2x_kb_bytes; w_lo = w_hi + p.w2x_res_plane; w_hib = w_hi + hq * p.w2x_res_plane; }
         } else {
             mbar_wait(&w_full[wstage], wphase);
             tc_fence_after();
             w_hi = w_area_u + wstage * p.w_stage_bytes;
             w_lo = w_hi + p.w_plane_bytes;
+            w_hib = w_hi + hq * p.w_plane_bytes;
         }
     };
     auto w_done = [&]() {
@@ -144,9 +152,9 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
             const uint32_t a_hi = p.raw ? e_ring_u + astage * p.e_stage_bytes : a_ring_u + astage * p.a_stage_bytes;
             const uint32_t lo_off = p.raw ? (p.e_split ? p.e_plane_bytes : 0u) : (p.a_has_lo ? p.a_plane_bytes : 0u);
             for (int j = 0; j < p.taps; ++j) {
-                uint32_t w_hi, w_lo;
-                w_get(0, j * p.chunks1 + cc, w_hi, w_lo);
-                issue_blocks<KA>(leader, p.G, d0, p.ch, a_hi + j * p.dil * row_bytes, lo_off, w_hi, w_lo, p.w1_split != 0, idesc1, acc);
+                uint32_t w_hi, w_lo, w_hib;
+                w_get(0, j * p.chunks1 + cc, w_hi, w_lo, w_hib);
+                issue_blocks<KA>(leader, p.G, d0, p.ch, a_hi + j * p.dil * row_bytes, lo_off, w_hi, w_lo, p.w1_split != 0, idesc1, acc, w_hib, idesc1_lo);
                 acc = 1u;
                 w_done();
             }
@@ -165,9 +173,9 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
         const uint32_t hbase = h_u + hb * p.h_stage_bytes;
         uint32_t acc = 0;
         for (int kb = 0; kb < p.hblocks; ++kb) {
-            uint32_t w_hi, w_lo;
-            w_get(1, kb, w_hi, w_lo);
-            issue_blocks<KH>(leader, p.G, acc2, p.cout, hbase + kb * p.h_blk_bytes, p.h_split ? p.h_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
+            uint32_t w_hi, w_lo, w_hib;
+            w_get(1, kb, w_hi, w_lo, w_hib);
+            issue_blocks<KH>(leader, p.G, acc2, p.cout, hbase + kb * p.h_blk_bytes, p.h_split ? p.h_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc, w_hib, idesc2_lo);
             acc = 1u;
             w_done();
         }
@@ -177,10 +185,10 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
             for (int cc = 0; cc < p.chunks1; ++cc) {
                 int st = a_base[it & 1] + cc;
                 if (st >= p.a_stages) st -= p.a_stages;
-                uint32_t w_hi, w_lo;
-                w_get(2, cc, w_hi, w_lo);
+                uint32_t w_hi, w_lo, w_hib;
+                w_get(2, cc, w_hi, w_lo, w_hib);
                 issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + st * p.a_stage_bytes + p.sc_row_off * row_bytes,
-                                 p.a_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
+                                 p.a_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc, w_hib, idesc2_lo);
                 acc = 1u;
                 w_done();
                 if (leader) umma_commit(&a_empty[st]);
@@ -189,9 +197,9 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
             for (int cc = 0; cc < p.xchunks; ++cc) {
                 mbar_wait(&a_full[astage], aphase);
                 tc_fence_after();
-                uint32_t w_hi, w_lo;
-                w_get(2, cc, w_hi, w_lo);
-                issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + astage * p.a_stage_bytes, p.x_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc);
+                uint32_t w_hi, w_lo, w_hib;
+                w_get(2, cc, w_hi, w_lo, w_hib);
+                issue_blocks<KA>(leader, p.G, acc2, p.cout, a_ring_u + astage * p.a_stage_bytes, p.x_has_lo ? p.a_plane_bytes : 0u, w_hi, w_lo, p.w2_split != 0, idesc2, acc, w_hib, idesc2_lo);
                 acc = 1u;
                 w_done();
                 if (leader) umma_commit(&a_empty[astage]);
@@ -369,38 +377,35 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             const uint32_t blk1 = p.ch * row_bytes, blk2h = p.cout * p.bkh * 2, blk2x = p.cout * row_bytes;
             const int nkb1 = p.taps * p.chunks1;
             if (p.w_resident) {
-                mbar_arrive_expect_tx(wres_bar, (uint32_t)nkb1 * blk1 * (1 + p.w1_split) +
-                                                    ((uint32_t)p.hblocks * blk2h + (uint32_t)p.xchunks * blk2x) * (1 + p.w2_split));
-                for (int kb = 0; kb < nkb1; ++kb) {
-                    tma_load_2d(w_area + (size_t)kb * p.w1_kb_bytes, &maps.w1, wres_bar, kb * p.bk, 0);
-                    if (p.w1_split) tma_load_2d(w_area + p.w1_res_plane + (size_t)kb * p.w1_kb_bytes, &maps.w1, wres_bar, kb * p.bk, p.ch);
-                }
-                for (int kb = 0; kb < p.hblocks; ++kb) {
-                    tma_load_2d(w_area + p.w2h_res_off + (size_t)kb * p.w2h_kb_bytes, &maps.w2h, wres_bar, kb * p.bkh, 0);
-                    if (p.w2_split) tma_load_2d(w_area + p.w2h_res_off + p.w2h_res_plane + (size_t)kb * p.w2h_kb_bytes, &maps.w2h, wres_bar, kb * p.bkh, p.cout);
-                }
-                for (int cc = 0; cc < p.xchunks; ++cc) {
-                    tma_load_2d(w_area + p.w2x_res_off + (size_t)cc * p.w2x_kb_bytes, &maps.w2x, wres_bar, p.ch + cc * p.bk, 0);
-                    if (p.w2_split) tma_load_2d(w_area + p.w2x_res_off + p.w2x_res_plane + (size_t)cc * p.w2x_kb_bytes, &maps.w2x, wres_bar, p.ch + cc * p.bk, p.cout);
-                }
+                const int pl1 = 1 + p.w1_split + p.w1_hib, pl2 = 1 + p.w2_split + p.w2_hib;
+                mbar_arrive_expect_tx(wres_bar, (uint32_t)nkb1 * blk1 * pl1 + ((uint32_t)p.hblocks * blk2h + (uint32_t)p.xchunks * blk2x) * pl2);
+                for (int kb = 0; kb < nkb1; ++kb)
+                    for (int q = 0; q < pl1; ++q)
+                        tma_load_2d(w_area + (size_t)q * p.w1_res_plane + (size_t)kb * p.w1_kb_bytes, &maps.w1, wres_bar, kb * p.bk, q * p.ch);
+                for (int kb = 0; kb < p.hblocks; ++kb)
+                    for (int q = 0; q < pl2; ++q)
+                        tma_load_2d(w_area + p.w2h_res_off + (size_t)q * p.w2h_res_plane + (size_t)kb * p.w2h_kb_bytes, &maps.w2h, wres_bar, kb * p.bkh, q * p.cout);
+                for (int cc = 0; cc < p.xchunks; ++cc)
+                    for (int q = 0; q < pl2; ++q)
+                        tma_load_2d(w_area + p.w2x_res_off + (size_t)q * p.w2x_res_plane + (size_t)cc * p.w2x_kb_bytes, &maps.w2x, wres_bar, p.ch + cc * p.bk, q * p.cout);
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
-                auto put = [&](const CUtensorMap* map, int col, uint32_t blk, int split, int rows) {
+                auto put = [&](const CUtensorMap* map, int col, uint32_t blk, int planes, int rows) {
                     mbar_wait(&w_empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&w_full[stage], blk * (1 + split));
+                    mbar_arrive_expect_tx(&w_full[stage], blk * planes);
                     uint8_t* dst = w_area + (size_t)stage * p.w_stage_bytes;
-                    tma_load_2d(dst, map, &w_full[stage], col, 0);
-                    if (split) tma_load_2d(dst + p.w_plane_bytes, map, &w_full[stage], col, rows);
+                    for (int q = 0; q < planes; ++q) tma_load_2d(dst + (size_t)q * p.w_plane_bytes, map, &w_full[stage], col, q * rows);
                     if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
                 };
+                const int pl1 = 1 + p.w1_split + p.w1_hib, pl2 = 1 + p.w2_split + p.w2_hib;
                 auto put1 = [&]() {
                     for (int cc = 0; cc < p.chunks1; ++cc)
-                        for (int j = 0; j < p.taps; ++j) put(&maps.w1, (j * p.chunks1 + cc) * p.bk, blk1, p.w1_split, p.ch);
+                        for (int j = 0; j < p.taps; ++j) put(&maps.w1, (j * p.chunks1 + cc) * p.bk, blk1, pl1, p.ch);
                 };
                 auto put2 = [&]() {
-                    for (int kb = 0; kb < p.hblocks; ++kb) put(&maps.w2h, kb * p.bkh, blk2h, p.w2_split, p.cout);
-                    for (int cc = 0; cc < p.xchunks; ++cc) put(&maps.w2x, p.ch + cc * p.bk, blk2x, p.w2_split, p.cout);
+                    for (int kb = 0; kb < p.hblocks; ++kb) put(&maps.w2h, kb * p.bkh, blk2h, pl2, p.cout);
+                    for (int cc = 0; cc < p.xchunks; ++cc) put(&maps.w2x, p.ch + cc * p.bk, blk2x, pl2, p.cout);
                 };
                 if (p.dbl) {
                     if (my_tiles > 0) put1();
@@ -518,7 +523,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                 apply_act(o, p.act1, alpha1_s, ralpha1_s, col);
                 uint32_t hi[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hi[i] = pack_bf16(o[2 * i], o[2 * i + 1]);
+                for (int i = 0; i < 8; ++i) hi[i] = pack16(o[2 * i], o[2 * i + 1], p.f16 != 0);
                 const int kb = col / p.bkh;
                 const int u0 = (col % p.bkh) >> 3;
                 const int xr = (row >> xshift) & (units_per_row - 1);
@@ -529,8 +534,8 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                     uint32_t lo[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&hi[i]);
-                        lo[i] = pack_bf16(o[2 * i] - __low2float(h2), o[2 * i + 1] - __high2float(h2));
+                        const float2 hf = unpack16(hi[i], p.f16 != 0);
+                        lo[i] = pack_bf16(o[2 * i] - hf.x, o[2 * i + 1] - hf.y);
                     }
                     *reinterpret_cast<uint4*>(rowp + p.h_plane_bytes + (((u0) ^ xr) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(rowp + p.h_plane_bytes + (((u0 + 1) ^ xr) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
@@ -582,13 +587,13 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                 float o[16];
                 add_bias16(o, v, bias2_s + col);
                 if (has_res) {
-                    add_bf16x16(o, rcur[0], rcur[1]);
+                    add_bf16x16(o, rcur[0], rcur[1], p.res_f16 != 0);
                     if (has_res_lo) add_bf16x16(o, rcur[2], rcur[3]);
                 }
-                if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr);
+                if (p.y) store_bf16x16(o, p.y + (long long)b * p.y_bs + flat, p.y_lo ? p.y_lo + (long long)b * p.y_bs + flat : nullptr, p.y_f16 != 0);
                 if (p.y_act) {
                     apply_act(o, p.act2, alpha2_s, ralpha2_s, col);
-                    store_bf16x16(o, p.y_act + (long long)b * p.ya_bs + flat, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + flat : nullptr);
+                    store_bf16x16(o, p.y_act + (long long)b * p.ya_bs + flat, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + flat : nullptr, p.ya_f16 != 0);
                 }
             }
             tc_fence_before();
@@ -658,6 +663,12 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     AC_REQUIRE(encode, "ac_resunit_tc: cuTensorMapEncodeTiled not available");
 
     const int w1_split = d->w1_split ? 1 : 0, w2_split = d->w2_split ? 1 : 0, h_split = d->h_split ? 1 : 0;
+    const int f16 = (d->fmt & AC_FMT_A_F16) ? 1 : 0, w1_hib = (d->fmt & AC_FMT_W_HIB) ? 1 : 0, w2_hib = (d->fmt & AC_FMT_W2_HIB) ? 1 : 0;
+    AC_REQUIRE(f16 || !(w1_hib | w2_hib), "ac_resunit_tc: the extra bf16(W) planes only exist for fp16 operands");
+    AC_REQUIRE(!f16 || d->act0 == AC_ACT_NONE, "ac_resunit_tc: raw mode (act0) is bf16 only");
+    AC_REQUIRE(!f16 || ((!d->a_lo || w1_hib) && (!(h_split || (d->x && d->x_lo)) || w2_hib)),
+               "ac_resunit_tc: fp16 operands with a lo plane need the bf16(W) plane of that GEMM");
+    const int pl1 = 1 + w1_split + w1_hib, pl2 = 1 + w2_split + w2_hib;
     const int a_has_lo = d->a_lo ? 1 : 0, x_has_lo = (d->x && d->x_lo) ? 1 : 0, has_x = (d->x || d->x_from_a) ? 1 : 0;
     const int any_lo = a_has_lo | x_has_lo;
     const int sms = sm_count();
@@ -687,7 +698,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
             const int nkb1 = d->taps * chunks1;
             const uint32_t w1_kb = round_up((uint32_t)d->ch * bk * 2, 1024), w2h_kb = round_up((uint32_t)d->cout * bkh * 2, 1024),
                            w2x_kb = round_up((uint32_t)d->cout * bk * 2, 1024);
-            const size_t w_res_total = (size_t)nkb1 * w1_kb * (1 + w1_split) + ((size_t)hblocks * w2h_kb + (size_t)xchunks * w2x_kb) * (1 + w2_split);
+            const size_t w_res_total = (size_t)nkb1 * w1_kb * pl1 + ((size_t)hblocks * w2h_kb + (size_t)xchunks * w2x_kb) * pl2;
             const bool resident = w_res_total <= 64 * 1024;
             for (int G : {4, 2, 1}) {
                 if (g_only > 0 && G != g_only) continue;
@@ -709,7 +720,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 const size_t h_total = h_stage * (1 + dbl);
                 uint32_t w_plane = w1_kb > w2h_kb ? w1_kb : w2h_kb;
                 if (xchunks && w2x_kb > w_plane) w_plane = w2x_kb;
-                const uint32_t w_stage = w_plane * (1 + (w1_split | w2_split));
+                const uint32_t w_stage = w_plane * (pl1 > pl2 ? pl1 : pl2);
                 uint32_t cols = 32;
                 while (cols < (uint32_t)need_cols) cols <<= 1;
                 const size_t budget = SMEM_LIMIT - fixed;
@@ -743,8 +754,8 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 p.a_stage_bytes = a_stage_raw; p.a_plane_bytes = a_plane; p.e_stage_bytes = e_stage; p.e_plane_bytes = a_plane; p.w_stage_bytes = w_stage; p.w_plane_bytes = w_plane;
                 p.w1_kb_bytes = w1_kb; p.w2h_kb_bytes = w2h_kb; p.w2x_kb_bytes = w2x_kb;
                 p.w1_res_plane = (uint32_t)nkb1 * w1_kb; p.w2h_res_plane = (uint32_t)hblocks * w2h_kb; p.w2x_res_plane = (uint32_t)xchunks * w2x_kb;
-                p.w2h_res_off = (uint32_t)nkb1 * w1_kb * (1 + w1_split);
-                p.w2x_res_off = p.w2h_res_off + (uint32_t)hblocks * w2h_kb * (1 + w2_split);
+                p.w2h_res_off = (uint32_t)nkb1 * w1_kb * pl1;
+                p.w2x_res_off = p.w2h_res_off + (uint32_t)hblocks * w2h_kb * pl2;
                 p.w_area_bytes = (uint32_t)w_area;
                 p.h_blk_bytes = h_blk; p.h_plane_bytes = h_plane; p.h_stage_bytes = (uint32_t)h_stage;
                 p.dbl = dbl; p.acc1_stride = (uint32_t)G * d->ch;
@@ -779,16 +790,18 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
             AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (X lo) failed: %d", r);
         }
     }
-    r = encode_w_map(encode, &maps.w1, d->w1, d->taps * d->cin, d->ch, 1 + w1_split, p.bk);
+    r = encode_w_map(encode, &maps.w1, d->w1, d->taps * d->cin, d->ch, pl1, p.bk);
     AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (W1) failed: %d", r);
-    r = encode_w_map(encode, &maps.w2h, d->w2, d->ch + (has_x ? d->cin : 0), d->cout, 1 + w2_split, p.bkh);
+    r = encode_w_map(encode, &maps.w2h, d->w2, d->ch + (has_x ? d->cin : 0), d->cout, pl2, p.bkh);
     AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (W2 hidden part) failed: %d", r);
-    r = encode_w_map(encode, &maps.w2x, d->w2, d->ch + (has_x ? d->cin : 0), d->cout, 1 + w2_split, p.bk);
+    r = encode_w_map(encode, &maps.w2x, d->w2, d->ch + (has_x ? d->cin : 0), d->cout, pl2, p.bk);
     AC_REQUIRE(r == 0, "ac_resunit_tc: tensor map (W2 x part) failed: %d", r);
 
     p.raw = raw; p.act0 = d->act0; p.e_split = e_split; p.x_from_a = x_from_a; p.sc_row_off = d->x_row_off; p.alpha0 = d->alpha0;
     p.cin = d->cin; p.taps = d->taps; p.dil = d->dilation; p.shift = d->shift; p.a_has_lo = a_has_lo; p.x_has_lo = x_has_lo;
     p.ch = d->ch; p.cout = d->cout; p.h_split = h_split; p.w1_split = w1_split; p.w2_split = w2_split;
+    p.f16 = f16; p.w1_hib = w1_hib; p.w2_hib = w2_hib;
+    p.y_f16 = (d->fmt & AC_FMT_Y_F16) ? 1 : 0; p.ya_f16 = (d->fmt & AC_FMT_YACT_F16) ? 1 : 0; p.res_f16 = (d->fmt & AC_FMT_RES_F16) ? 1 : 0;
     p.m_rows = d->m_rows; p.m_groups = (d->m_rows + p.G * TILE_M - 1) / (p.G * TILE_M); p.batch = d->batch;
     p.bias1 = d->bias1; p.alpha1 = d->alpha1; p.bias2 = d->bias2; p.alpha2 = d->alpha2; p.act1 = d->act1; p.act2 = d->act2;
     p.res = (const __nv_bfloat16*)d->res; p.res_lo = (const __nv_bfloat16*)d->res_lo;

@@ -7,6 +7,7 @@
 // micro-tile of dot products, keeps a running best per frame, then the CTA reduces to the argmin with
 // the reference's tie rule (lowest index) and subtracts the selected codeword in place.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -130,7 +131,7 @@ __global__ void rvq_decode_f32_kernel(const int64_t* __restrict__ codes, const f
                                       float* __restrict__ out, int64_t rows, int dim, int n_codes, int stages,
                                       int code_stride, int code_offset, int* err_flag,
                                       __nv_bfloat16* __restrict__ out_bf = nullptr, int rows_per_clip = 1, long long bstride = 0,
-                                      __nv_bfloat16* __restrict__ out_lo = nullptr) {
+                                      __nv_bfloat16* __restrict__ out_lo = nullptr, int out_f16 = 0) {
     // one thread per VEC consecutive output channels; consecutive threads cover one row contiguously
     const int per_row = dim / VEC;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,9 +160,17 @@ __global__ void rvq_decode_f32_kernel(const int64_t* __restrict__ codes, const f
         const long long off = (row / rows_per_clip) * bstride + (row % rows_per_clip) * (long long)dim + d0;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const __nv_bfloat16 hb = __float2bfloat16(acc[v]);
-            out_bf[off + v] = hb;
-            if (out_lo) out_lo[off + v] = __float2bfloat16(acc[v] - __bfloat162float(hb));
+            float hv;
+            if (out_f16) {  // fp16 hi plane (saturating), bf16 lo plane
+                const __half hh = __float2half_rn(fminf(fmaxf(acc[v], -65504.f), 65504.f));
+                reinterpret_cast<__half*>(out_bf)[off + v] = hh;
+                hv = __half2float(hh);
+            } else {
+                const __nv_bfloat16 hb = __float2bfloat16(acc[v]);
+                out_bf[off + v] = hb;
+                hv = __bfloat162float(hb);
+            }
+            if (out_lo) out_lo[off + v] = __float2bfloat16(acc[v] - hv);
         }
     }
     if (!out) return;
@@ -223,13 +232,13 @@ extern "C" int ac_rvq_decode_f32(const int64_t* codes, const float* codebooks, f
 
 extern "C" int ac_rvq_decode_bf16(const int64_t* codes, const float* codebooks, void* out_bf16, void* out_lo, int64_t rows,
                                   int32_t rows_per_clip, int64_t bstride, int32_t dim, int32_t n_codes, int32_t stages,
-                                  int32_t code_stride, int32_t code_offset, int32_t* err_flag, void* stream) {
+                                  int32_t code_stride, int32_t code_offset, int32_t* err_flag, int32_t out_f16, void* stream) {
     AC_REQUIRE(codes && codebooks && out_bf16, "ac_rvq_decode_bf16: null pointer");
     AC_REQUIRE(rows > 0 && stages > 0 && dim > 0 && dim % 4 == 0 && rows_per_clip > 0, "ac_rvq_decode_bf16: bad sizes");
     const int threads = 256;
     const int64_t total = rows * (dim / 4);
     rvq_decode_f32_kernel<4><<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         codes, codebooks, nullptr, rows, dim, n_codes, stages, code_stride, code_offset, err_flag,
-        (__nv_bfloat16*)out_bf16, rows_per_clip, bstride, (__nv_bfloat16*)out_lo);
+        (__nv_bfloat16*)out_bf16, rows_per_clip, bstride, (__nv_bfloat16*)out_lo, out_f16);
     return ac::finish_launch("ac_rvq_decode_bf16");
 }

@@ -130,5 +130,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// same with A = B = IEEE fp16 (operand format fields 0).  Both operands of one MMA must share the format (a mixed pair is an
+// illegal instruction on this hardware -- measured); different MMAs into one accumulator may use different formats.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 }  // namespace sm100

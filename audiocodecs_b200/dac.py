@@ -97,11 +97,13 @@ class DAC(Codec):
                  state_dict=None, precision="exact", split_min_ch=512, split_res_min_ch=64, w_single=None):
         super().__init__(sample_rate, orig_sample_rate, mode)
         self.w_single = w_single
-        if precision not in ("exact", "fp32", "bf16"):
-            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
-                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
+        if precision not in ("exact", "fp16", "fp32", "bf16"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-precision encoder: reference tokens), 'fp16' "
+                             "(one fp16 product per MAC: fastest), 'bf16' (error-compensated bf16 products) or 'fp32' (SIMT path)")
         self.tensor_path = precision != "fp32"
         self.exact = precision == "exact"
+        if self.tensor_path:
+            self.pol_enc, self.pol_dec = tc.policies(precision, split_min_ch)
         # activated tensors (MMA operands) / raw residual-stream tensors with >= this many channels travel as (hi, lo) bf16 planes
         self.split_min_ch = split_min_ch
         self.split_res_min_ch = split_res_min_ch
@@ -109,7 +111,7 @@ class DAC(Codec):
         self.vocab_size = 1024
         self.latent = latent
         self.precision = precision
-        self.compute_dtype = "bf16" if self.tensor_path else "f32"
+        self.compute_dtype = {"exact": "f16", "fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision]
         tag = f"{int(orig_sample_rate / 1000)}khz"  # R/audiocodecs/dac.py:55
         if tag not in _ARCH:
             raise ValueError(f"no DAC model for {tag}")
@@ -122,11 +124,8 @@ class DAC(Codec):
             state_dict = dac.DAC.load(str(dac.utils.download(model_type=tag))).state_dict()
         self._build(descript_to_hf_keys(state_dict))
 
-    def _w_split(self, name):
-        # "exact": every encoder layer keeps the (hi, lo) weight pair (the tokens must be the reference's)
-        if self.exact and name.startswith("encoder"):
-            return True
-        return super()._w_split(name)
+    def _pol(self, name):
+        return self.pol_enc if name.startswith("encoder") else self.pol_dec
 
     # ------------------------------------------------------------------ packing
     def _conv(self, sd, prefix, stride=1, dilation=1, padding=0, snake=None, epi=EPI_NONE):
@@ -196,7 +195,7 @@ class DAC(Codec):
         """Conv1d [Cout,Cin,K] -> [Cout][K*Cin] (column = tap*Cin + c; a stride-s / kernel-2s conv read through the
         s-phase view has exactly this column order)."""
         w = packing.fold_weight_norm(sd, prefix)
-        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"], split=self._w_split(prefix))
+        W = self._pol(prefix).weights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".bias"], self._w_split(prefix))
         self._tcw.append(W)
         return W
 
@@ -210,7 +209,8 @@ class DAC(Codec):
         w_all[: S * D] = win.reshape(S * D, H)
         b_all = torch.zeros(n)
         b_all[: S * D] = self.b_in.reshape(-1)
-        self._tproj = TcWeights(w_all.float(), b_all)
+        # three products whatever the mode (a tiny GEMM whose rounding lands directly on the 8-dimensional decision)
+        self._tproj = TcWeights(w_all.float(), b_all, split=True, f16=self.pol_enc.f16, hib=self.pol_enc.f16)
         self._tcw.append(self._tproj)
         cross = torch.einsum("kdc,jce->kjde", win, wout)                  # [S,S,8,8]
         v = torch.einsum("kdc,jc->kjd", win, bout)                        # [S,S,8]
@@ -224,7 +224,7 @@ class DAC(Codec):
     def _tcw_convtr(self, sd, prefix, stride):
         w = packing.fold_weight_norm(sd, prefix)     # [Cin, Cout, 2s]
         pk = packing.pack_convtr(w, stride)          # [2, Cin, s*Cout]
-        W = TcWeights(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride), split=self._w_split(prefix))
+        W = self._pol(prefix).weights(pk.permute(2, 0, 1).reshape(pk.shape[2], -1), sd[prefix + ".bias"].float().repeat(stride), self._w_split(prefix))
         self._tcw.append(W)
         return W
 
@@ -252,17 +252,17 @@ class DAC(Codec):
                 p = f"decoder.block.{i}"
                 self._tdec.append((self._alpha(sd, p + ".snake1"), self._tcw_convtr(sd, p + ".conv_t1", s), s, self._tc_units(sd, p)))
             self._tdec_last_alpha = self._alpha(sd, "decoder.snake1")
-            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1])  # Cout = 1 as a stride-16 conv with 16 outputs
+            pd = self.pol_dec  # Cout = 1 as a stride-16 conv with 16 outputs
+            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1], split=True if pd.w_split is None else pd.w_split, f16=pd.f16)
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
-    def _split(self, C, enc=False):
-        return (enc and self.exact) or C >= self.split_min_ch
-
-    def _split_res(self, C, enc=False):
-        return (enc and self.exact) or C >= self.split_res_min_ch
+    def _split_res(self, pol, C):
+        """the raw residual stream (touched by epilogues only, never an MMA operand): lo plane from 64 channels up"""
+        return pol.full or C >= self.split_res_min_ch
 
     def _tc_run_units(self, units, x, xs, next_alpha, out_halo=(0, 0), enc=False):
+        pol = self.pol_enc if enc else self.pol_dec
         """three DacResidualUnits (HF/dac:173-207): x raw, xs = snake1(x) -> (y raw, ys = next_alpha-snake(y)).  The k7
         conv reads its 7 dilated taps from ONE staged block of xs (zero padding = TMA out-of-bounds fill); the 1x1 conv
         adds the residual and writes the raw stream plus the activation its consumer applies."""
@@ -271,19 +271,19 @@ class DAC(Codec):
         for i, (a1, W7, d, a2, W1) in enumerate(units):
             last = i == len(units) - 1
             nxt = next_alpha if last else units[i + 1][0]
-            y = None if last else Act(B, L, C, dev, split=self._split_res(C, enc))
+            y = None if last else pol.act(B, L, C, dev, split=self._split_res(pol, C))
             hl, hr = out_halo if last else (0, 0)
-            ys = Act(B, L, C, dev, hl=hl, hr=hr, split=self._split(C, enc))
+            ys = pol.act(B, L, C, dev, hl=hl, hr=hr)
             a = Src(xs, taps=7, dilation=d, shift=-3 * d)
 
             def unfused(a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
-                hs = Act(B, L, C, dev, split=self._split(C, enc))
+                hs = pol.act(B, L, C, dev)
                 tc.conv_tc(W7, [a], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
                 tc.conv_tc(W1, [Src(hs)], L, res=x, y=y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
 
             def fused(g, dbl, a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
                 return lambda: tc.resunit_tc(W7, W1, a, L, res=x, y=y, y_act=ys, act1=ACT_SNAKE, alpha1=a2.t, act2=ACT_SNAKE,
-                                             alpha2=nxt.t, h_split=self._split(C, enc), g_hint=g, dbl_hint=dbl, name="resunit_tc")
+                                             alpha2=nxt.t, h_split=pol.split(C), g_hint=g, dbl_hint=dbl, name="resunit_tc")
 
             # one fused launch (hidden tensor on chip) when both accumulators fit tensor memory, or two tap-GEMM launches.
             # Encoder: fused whenever it fits -- a rule, because the two forms group the fp32 accumulation differently and a
@@ -293,7 +293,7 @@ class DAC(Codec):
             if 2 * C <= 512:
                 fv = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)]
                 variants = fv if enc else fv + variants
-            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc), variants)
+            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc, xs.f16), variants)
             x, xs = y, ys
         return xs
 
@@ -301,8 +301,9 @@ class DAC(Codec):
         B, T = sig.shape
         dev = sig.device
         C = self._enc[0].cout
-        x = Act(B, T, C, dev, split=self._split_res(C, True) and self.exact)   # "bf16": the first layer's outputs stay single planes
-        xs = Act(B, T, C, dev, split=self._split(C, True) and self.exact)
+        pol = self.pol_enc
+        x = pol.act(B, T, C, dev, split=pol.full)   # not "exact": the first layer's outputs stay single planes
+        xs = pol.act(B, T, C, dev, split=pol.full)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xs, act=ACT_SNAKE, alpha=self._tenc[0][0][0][0].t)
         L = T
         for bi, (units, a_down, Wdown, s) in enumerate(self._tenc):
@@ -314,13 +315,13 @@ class DAC(Codec):
             C = 2 * C
             nxt = self._tenc[bi + 1][0][0][0] if bi + 1 < len(self._tenc) else self._tenc_last[0]
             last = bi + 1 == len(self._tenc)
-            x = None if last else Act(B, Lout, C, dev, split=self._split_res(C, True))
-            xs = Act(B, Lout, C, dev, split=self._split(C, True))
+            x = None if last else pol.act(B, Lout, C, dev, split=self._split_res(pol, C))
+            xs = pol.act(B, Lout, C, dev)
             tc.conv_tc(Wdown, [Src(ys, taps=2, origin=-p, phases=s, rows=(p + L + hr) // s)], Lout, y=x, y_act=xs, act=ACT_SNAKE,
                        alpha=nxt.t, name="down_tc")
             L = Lout
         if proj:  # latents as a split-bf16 activation -> all RVQ stages' in_proj in one GEMM: [B, L, 8S (padded to 16)] fp32
-            za = Act(B, L, C, dev, split=True)
+            za = pol.act(B, L, C, dev, split=True)
             tc.conv_tc(self._tenc_last[1], [Src(xs, taps=3, shift=-1)], L, y=za, name="conv_k3_tc")
             P = torch.empty((B, L, self._tproj.n_total), device=dev, dtype=torch.float32)
             tc.conv_tc(self._tproj, [Src(za)], L, y32=P, name="rvq_in_proj_tc")
@@ -332,18 +333,19 @@ class DAC(Codec):
     def _decoder_tc(self, zq):
         B, N, C = zq.shape
         dev = zq.device
-        z = Act(B, N, C, dev, split=True)
+        pol = self.pol_dec
+        z = pol.act(B, N, C, dev)
         ops.f32_to_act(zq.contiguous(), z)
         C = self._tdec_first.n_total
-        xs = Act(B, N, C, dev, split=self._split(C))
+        xs = pol.act(B, N, C, dev)
         tc.conv_tc(self._tdec_first, [Src(z, taps=7, shift=-3)], N, y_act=xs, act=ACT_SNAKE, alpha=self._tdec[0][0].t, name="conv_k7_tc")
         L = N
         for bi, (a_up, Wtr, s, units) in enumerate(self._tdec):
             p = math.ceil(s / 2)
             C = C // 2
             Lout = L * s + s - 2 * p  # (L - 1) s - 2 p + 2 s: L s, or L s - 1 for an odd stride
-            x = Act(B, Lout, C, dev, split=self._split_res(C))
-            us = Act(B, Lout, C, dev, split=self._split(C))
+            x = pol.act(B, Lout, C, dev, split=self._split_res(pol, C))
+            us = pol.act(B, Lout, C, dev)
             # transposed conv (k = 2s, stride s, padding p): 2-tap GEMM over n = (phase, cout), flat output shifted by p*C
             tc.conv_tc(Wtr, [Src(xs, taps=2, shift=-1)], L + 1, y=x, y_act=us, act=ACT_SNAKE, alpha=units[0][0].t, act_mod=C,
                        out_rows=Lout, out_ch=C, out_shift=p * C, name="convtr_tc")

@@ -34,11 +34,13 @@ class Encodec(Codec):
     R/audiocodecs/encodec.py:51) and only its state dict is kept.
 
     `precision`:
-      "exact" (default) tcgen05 tensor path whose ENCODER carries every activation and weight as a (hi, lo) bf16 pair
-              (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulate; fp16 LSTM recurrence): embeddings within ~2e-5 of the
-              fp32 reference, so the tokens equal the reference's wherever its top-2 distance gap exceeds 1e-4.  The
-              decoder is the "bf16" one (waveform SI-SNR >= 40 dB).
-      "bf16"  fastest: (hi, lo) pairs only where the waveform SI-SNR needs them; ~95 % of the tokens equal the reference's.
+      "exact" (default) tcgen05 tensor path whose ENCODER carries every activation as an (fp16 hi, bf16 lo) pair and every
+              weight as an fp16 (hi, lo) pair: A_hi W_hi + A_hi W_lo + A_lo bf16(W), fp32 accumulate, ~2^-20 operand
+              precision (+ fp16 LSTM recurrence): embeddings within ~1e-5 of the fp32 reference, so the tokens equal the
+              reference's wherever its top-2 distance gap exceeds 1e-4.  The decoder is the "fp16" one.
+      "fp16"  fastest: ONE fp16 product per MAC (11-bit operands, fp32 accumulate): decoder SI-SNR ~55 dB, ~98.5 % of the
+              tokens equal the reference's.
+      "bf16"  the error-compensated bf16 path of round 1 (two to three bf16 products per MAC; kept for comparison).
       "fp32"  SIMT fp32 kernels (debugging / parity reference; ~15x slower).
     """
 
@@ -55,14 +57,16 @@ class Encodec(Codec):
         if use_vocos:
             raise NotImplementedError("the Vocos decoder branch (R/audiocodecs/encodec.py:53-66) is outside this build")
         self.num_codebooks = num_codebooks
-        if precision not in ("exact", "bf16", "fp32"):
-            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
-                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
+        if precision not in ("exact", "fp16", "bf16", "fp32"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-precision encoder: reference tokens), 'fp16' "
+                             "(tcgen05 tensor path, one fp16 product per MAC: fastest), 'bf16' (error-compensated bf16 products) "
+                             "or 'fp32' (SIMT path)")
         self.precision = precision
         self.tensor_path = precision != "fp32"
         self.exact = precision == "exact"
-        self.enc_split_min = 0 if self.exact else SPLIT_MIN_CH
-        self.compute_dtype = "bf16" if self.tensor_path else "f32"
+        if self.tensor_path:
+            self.pol_enc, self.pol_dec = tc.policies(precision, SPLIT_MIN_CH)
+        self.compute_dtype = {"exact": "f16", "fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision]
         self.use_vocos = use_vocos
         self.vocab_size = 1024
         tag = int(orig_sample_rate / 1000)
@@ -163,18 +167,21 @@ class Encodec(Codec):
         return self._specs + self._tcw
 
     # ------------------------------------------------------------------ bf16 tensor-path packing
+    def _pol(self, prefix):
+        return self.pol_enc if prefix.startswith("encoder") else self.pol_dec
+
     def _tc_conv(self, sd, prefix):
         """Conv1d [Cout,Cin,K] -> bf16 [Cout][K*Cin] (column = tap*Cin + c; a stride-s/kernel-2s conv read through the
         s-phase view has exactly this column order)."""
         w = packing.fold_weight_norm(sd, prefix + ".conv")
-        W = TcWeights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".conv.bias"], split=self._w_split(prefix))
+        W = self._pol(prefix).weights(w.permute(0, 2, 1).reshape(w.shape[0], -1), sd[prefix + ".conv.bias"], self._w_split(prefix))
         self._tcw.append(W)
         return W
 
     def _tc_convtr(self, sd, prefix, stride):
         w = packing.fold_weight_norm(sd, prefix + ".conv")  # [Cin, Cout, 2s]
         p = packing.pack_convtr(w, stride)                  # [2, Cin, s*Cout]
-        W = TcWeights(p.permute(2, 0, 1).reshape(p.shape[2], -1), sd[prefix + ".conv.bias"].float().repeat(stride), split=self._w_split(prefix))
+        W = self._pol(prefix).weights(p.permute(2, 0, 1).reshape(p.shape[2], -1), sd[prefix + ".conv.bias"].float().repeat(stride), self._w_split(prefix))
         self._tcw.append(W)
         return W
 
@@ -183,19 +190,19 @@ class Encodec(Codec):
         wsc = packing.fold_weight_norm(sd, prefix + ".shortcut.conv")[:, :, 0]
         w1 = packing.fold_weight_norm(sd, prefix + ".block.3.conv")[:, :, 0]
         # second GEMM of the fused unit: columns = [hidden (conv_k1) | raw x (1x1 shortcut)], the two biases summed
-        tail = TcWeights(torch.cat([w1, wsc], dim=1), sd[prefix + ".shortcut.conv.bias"] + sd[prefix + ".block.3.conv.bias"],
-                         split=self._w_split(prefix + ".tail"))
+        tail = self._pol(prefix).weights(torch.cat([w1, wsc], dim=1), sd[prefix + ".shortcut.conv.bias"] + sd[prefix + ".block.3.conv.bias"],
+                                         self._w_split(prefix + ".tail"))
         self._tcw.append(tail)
         return k3, tail
 
-    def _tc_lstm(self, sd, prefix, exact=False):
+    def _tc_lstm(self, sd, prefix):
         out = []
         for l in range(2):
             # decoder / "bf16" encoder: single bf16 product for the input projection (a split changes the decoder SI-SNR by
             # < 0.1 dB: 45.1 -> 45.1 dB).  "exact" encoder: three products -- with one the embedding error is 1.8e-4 instead of
             # 1.9e-5 and 0.15 % of the safe tokens flip (scripts/exact_mode_emulation.py)
-            W = TcWeights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"],
-                          split=exact)
+            W = self._pol(prefix).weights(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.bias_ih_l{l}"] + sd[f"{prefix}.lstm.bias_hh_l{l}"],
+                                          False)
             self._tcw.append(W)
             out.append(W)
         return out
@@ -206,7 +213,7 @@ class Encodec(Codec):
             for r in reversed(RATIOS):
                 self._tenc.append((self._tc_resblock(sd, f"encoder.layers.{idx}"), self._tc_conv(sd, f"encoder.layers.{idx + 2}"), r))
                 idx += 3
-            self._tenc_lstm = self._tc_lstm(sd, f"encoder.layers.{idx}", exact=self.exact)
+            self._tenc_lstm = self._tc_lstm(sd, f"encoder.layers.{idx}")
             self._tenc_last = self._tc_conv(sd, f"encoder.layers.{idx + 2}")
         if self.mode != "encode":
             self._tdec_first = self._tc_conv(sd, "decoder.layers.0")
@@ -215,18 +222,20 @@ class Encodec(Codec):
             for r in RATIOS:
                 self._tdec.append((self._tc_convtr(sd, f"decoder.layers.{idx}", r), self._tc_resblock(sd, f"decoder.layers.{idx + 1}"), r))
                 idx += 3
-            self._tdec_last = tc.last_conv_weights_phased(self._dec_last)  # Cout = 1 as a stride-16 conv with 16 outputs
+            pd = self.pol_dec  # Cout = 1 as a stride-16 conv with 16 outputs
+            self._tdec_last = tc.last_conv_weights_phased(self._dec_last, split=True if pd.w_split is None else pd.w_split, f16=pd.f16)
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor-path execution
-    def _tc_run_lstm(self, Ws, whh, x: Act, final: Act, exact=False):
-        """x raw [B,N,512] -> final = ELU(lstm(x) + x) (HF/encodec:236-249 + the following ELU).  exact: the input
-        projections read the (hi, lo) pairs of x / h0 (three products)."""
+    def _tc_run_lstm(self, Ws, whh, x: Act, final: Act, pol):
+        """x raw [B,N,512] -> final = ELU(lstm(x) + x) (HF/encodec:236-249 + the following ELU).  With the "exact" encoder
+        policy the input projections read the (hi, lo) pairs of x / h0 (three products)."""
         B, N, C = x.B, x.L, x.C
         dev = x.buf.device
+        exact = pol.full
         pre = torch.empty((B, N, 4 * C), device=dev, dtype=torch.float32)
         tc.conv_tc(Ws[0], [Src(x if exact else x.hi_only())], N, y32=pre, name="lstm_ih_tc")
-        h0 = Act(B, N, C, dev, split=True)   # "bf16": the lo plane matters for the skip-add of the last layer's h only
+        h0 = pol.act(B, N, C, dev, split=True)   # not "exact": the lo plane matters for the skip-add of the last layer's h only
         ops.lstm_tc(pre, getattr(self, whh[0] + "_16"), out=h0)
         tc.conv_tc(Ws[1], [Src(h0 if exact else h0.hi_only())], N, y32=pre, name="lstm_ih_tc")
         # the skip-add + ELU runs as its own HBM-bound pass: inside the recurrence kernel its loads/stores sat on the
@@ -234,14 +243,14 @@ class Encodec(Codec):
         ops.lstm_tc(pre, getattr(self, whh[1] + "_16"), out=h0)
         ops.add_act_bf16(h0, x, final, ACT_ELU)
 
-    def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act, split_min=SPLIT_MIN_CH):
+    def _tc_resblock_run(self, Wk3, Wtail, x: Act, xe: Act, ye: Act, pol):
         """x raw, xe = ELU(x) with a 2-row reflect halo -> ye = ELU(shortcut(x) + conv1(ELU(conv3(xe)))).
         Either ONE fused launch with the hidden activation kept on chip (ac_resunit_tc; tile grouping and double
         buffering tuned per shape) or two tap-GEMM launches -- whichever measures faster for this layer shape.
         xe is None in raw mode (C <= RAW_MAX_CH): x itself carries the 2-row halo, the kernel applies the input ELU on
         chip and reads the raw rows of the same staged blocks for the shortcut."""
         B, L, C = x.B, x.L, x.C
-        hs = C // 2 >= split_min
+        hs = pol.split(C // 2)
         if xe is None:
             x.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
             a = Src(x, taps=3, origin=-2, rows=L + 2)
@@ -256,7 +265,7 @@ class Encodec(Codec):
         a = Src(xe, taps=3, origin=-2, rows=L + 2)
 
         def unfused():
-            he = Act(B, L, C // 2, x.buf.device, split=hs)
+            he = pol.act(B, L, C // 2, x.buf.device, split=hs)
             tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
             tc.conv_tc(Wtail, [Src(he), Src(x)], L, y_act=ye, act=ACT_ELU, name="res_tail_tc")
 
@@ -269,33 +278,33 @@ class Encodec(Codec):
             variants.append(("unfused", unfused))
         elif C > FUSED_MAX_CH:
             variants = [("unfused", unfused)]
-        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None, hs), variants)
+        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None, hs, x.f16), variants)
 
     def _encoder_tc(self, sig, vlen=None):
         B, T = sig.shape
         dev = sig.device
         raw = 32 <= RAW_MAX_CH
-        smin = self.enc_split_min
-        x = Act(B, T, 32, dev, hl=2 if raw else 0, split=32 >= smin)
-        xe = None if raw else Act(B, T, 32, dev, hl=2, split=32 >= smin)
+        pol = self.pol_enc
+        x = pol.act(B, T, 32, dev, hl=2 if raw else 0)
+        xe = None if raw else pol.act(B, T, 32, dev, hl=2)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU, vlen=vlen)
         L = T
         for i, ((Wk3, Wtail), Wdown, r) in enumerate(self._tenc):
             C = x.C
             Lout = -(-L // r)
             extra = Lout * r - L
-            ye = Act(B, L, C, dev, hl=r, hr=extra, split=C >= smin)
-            self._tc_resblock_run(Wk3, Wtail, x, xe, ye, split_min=smin)
+            ye = pol.act(B, L, C, dev, hl=r, hr=extra)
+            self._tc_resblock_run(Wk3, Wtail, x, xe, ye, pol)
             ye.fill_halo(PAD_REFLECT, max(r, extra) + 1 if L <= max(r, extra) else 0)
             last = i == len(self._tenc) - 1
             raw = not last and 2 * C <= RAW_MAX_CH
-            x = Act(B, Lout, 2 * C, dev, hl=2 if raw else 0, split=2 * C >= smin)
-            xe = None if (last or raw) else Act(B, Lout, 2 * C, dev, hl=2, split=2 * C >= smin)
+            x = pol.act(B, Lout, 2 * C, dev, hl=2 if raw else 0)
+            xe = None if (last or raw) else pol.act(B, Lout, 2 * C, dev, hl=2)
             tc.conv_tc(Wdown, [Src(ye, taps=2, origin=-r, phases=r, rows=Lout + 1)], Lout, y=x, y_act=xe, act=ACT_ELU,
                        name="down_tc")
             L = Lout
-        le = Act(B, L, x.C, dev, hl=6, split=True)
-        self._tc_run_lstm(self._tenc_lstm, [n for _, n in self._enc_lstm], x, le, exact=self.exact)
+        le = pol.act(B, L, x.C, dev, hl=6)
+        self._tc_run_lstm(self._tenc_lstm, [n for _, n in self._enc_lstm], x, le, pol)
         le.fill_halo(PAD_REFLECT, 7 if L <= 6 else 0)
         emb = torch.empty((B, L, 128), device=dev, dtype=torch.float32)
         tc.conv_tc(self._tenc_last, [Src(le, taps=7, origin=-6, rows=L + 6)], L, y32=emb, name="conv_k7_tc")
@@ -304,27 +313,27 @@ class Encodec(Codec):
     def _decoder_tc(self, toks):
         B, N, K = toks.shape
         dev = toks.device
-        z = Act(B, N, 128, dev, hl=6, split=True)
+        pol = self.pol_dec
+        z = pol.act(B, N, 128, dev, hl=6)
         ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks, K, z, err_flag=self._err)
         z.fill_halo(PAD_REFLECT, 7 if N <= 6 else 0)
-        d0 = Act(B, N, 512, dev, split=True)
+        d0 = pol.act(B, N, 512, dev)
         tc.conv_tc(self._tdec_first, [Src(z, taps=7, origin=-6, rows=N + 6)], N, y=d0, name="conv_k7_tc")
-        ye = Act(B, N, 512, dev, split=True)
-        self._tc_run_lstm(self._tdec_lstm, [n for _, n in self._dec_lstm], d0, ye)
+        ye = pol.act(B, N, 512, dev)
+        self._tc_run_lstm(self._tdec_lstm, [n for _, n in self._dec_lstm], d0, ye, pol)
         L = N
         for i, (Wtr, (Wk3, Wtail), r) in enumerate(self._tdec):
             C = ye.C // 2
             Lout = L * r
-            sp = C >= SPLIT_MIN_CH
             raw = C <= RAW_MAX_CH
-            x = Act(B, Lout, C, dev, hl=2 if raw else 0, split=sp)
-            xe = None if raw else Act(B, Lout, C, dev, hl=2, split=sp)
+            x = pol.act(B, Lout, C, dev, hl=2 if raw else 0)
+            xe = None if raw else pol.act(B, Lout, C, dev, hl=2)
             # transposed conv: 2-tap GEMM over n = (phase, cout); row -1 reads as zero (TMA OOB fill)
             tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C,
                        name="convtr_tc")
             last = i == len(self._tdec) - 1
-            ye = Act(B, Lout, C, dev, hl=6 if last else 0, hr=10 if last else 0, split=sp)
-            self._tc_resblock_run(Wk3, Wtail, x, xe, ye)
+            ye = pol.act(B, Lout, C, dev, hl=6 if last else 0, hr=10 if last else 0)
+            self._tc_resblock_run(Wk3, Wtail, x, xe, ye, pol)
             L = Lout
         # last layer (Cout = 1, k7, causal reflect padding in the 6 left halo rows) on the tap-GEMM kernel, 16 samples per
         # GEMM row; the 10 right halo rows only pad the buffer to whole 16-sample view rows (they meet zero weights)

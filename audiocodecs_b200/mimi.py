@@ -37,18 +37,19 @@ class Mimi(Codec):
                  w_single=None):
         super().__init__(sample_rate, 24000, mode)
         self.w_single = w_single
-        if precision not in ("exact", "fp32", "bf16"):
-            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-bf16 encoder: reference tokens), 'bf16' "
-                             "(tcgen05 tensor path, fastest) or 'fp32' (SIMT path)")
+        if precision not in ("exact", "fp16", "fp32", "bf16"):
+            raise ValueError("precision must be 'exact' (tcgen05 tensor path, split-precision encoder: reference tokens), 'fp16' "
+                             "(one fp16 product per MAC: fastest), 'bf16' (error-compensated bf16 products) or 'fp32' (SIMT path)")
         self.tensor_path = precision != "fp32"
         self.exact = precision == "exact"
-        self.enc_split_min = 0 if self.exact else SPLIT_MIN_CH
+        if self.tensor_path:
+            self.pol_enc, self.pol_dec = tc.policies(precision, SPLIT_MIN_CH)
         self.num_codebooks = num_codebooks
         self.vocab_size = 2048
         self.latent = latent
         self.precision = precision
         self._rope_cache = {}
-        self.compute_dtype = "bf16" if self.tensor_path else "f32"
+        self.compute_dtype = {"exact": "f16", "fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision]
         if state_dict is None:
             try:
                 from transformers import MimiModel
@@ -149,8 +150,14 @@ class Mimi(Codec):
         return self._specs + self._tcw
 
     # ------------------------------------------------------------------ bf16 tensor path: packing
+    def _pol(self, name):
+        """encoder side = everything that shapes the tokens (SEANet encoder, encoder transformer, downsample, quantizer input
+        projections); the rest is the decoder side"""
+        enc = name.startswith(("encoder", "downsample")) or "input_proj" in name
+        return self.pol_enc if enc else self.pol_dec
+
     def _tw(self, w, bias=None, name=""):
-        W = TcWeights(w, bias, split=self._w_split(name))
+        W = self._pol(name).weights(w, bias, self._w_split(name))
         self._tcw.append(W)
         return W
 
@@ -200,19 +207,20 @@ class Mimi(Codec):
                 self._tdec.append((self._tw_convtr(sd, f"decoder.layers.{idx}.conv", r), self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.1.conv"),
                                    self._tw_conv(sd, f"decoder.layers.{idx + 1}.block.3.conv"), r))
                 idx += 3
-            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1])  # Cout = 1 as a stride-16 conv with 16 outputs
+            pd = self.pol_dec  # Cout = 1 as a stride-16 conv with 16 outputs
+            self._tdec_last = tc.last_conv_weights_phased(self._dec[-1], split=True if pd.w_split is None else pd.w_split, f16=pd.f16)
             self._tcw.append(self._tdec_last)
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
-    def _tc_resblock(self, Wk3, Wk1, x, xe, ye, split_min=SPLIT_MIN_CH):
+    def _tc_resblock(self, Wk3, Wk1, x, xe, ye, pol):
         """MimiResnetBlock (HF/mimi:412-451), identity shortcut, causal zero padding (TMA out-of-bounds fill):
         x raw, xe = ELU(x) -> ye = ELU(x + conv_k1(ELU(conv_k3(xe))))."""
         B, L, C = x.B, x.L, x.C
-        hs = C // 2 >= split_min
+        hs = pol.split(C // 2)
         a = Src(xe, taps=3, shift=-2)
 
         def unfused():
-            he = Act(B, L, C // 2, x.buf.device, split=hs)
+            he = pol.act(B, L, C // 2, x.buf.device, split=hs)
             tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
             tc.conv_tc(Wk1, [Src(he)], L, res=x, y_act=ye, act=ACT_ELU, name="res_k1_tc")
 
@@ -226,16 +234,16 @@ class Mimi(Codec):
         variants = [("unfused", unfused)]
         if C <= 256:
             variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
-        tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs), variants)
+        tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs, x.f16), variants)
 
-    def _tc_transformer(self, layers, tws, h):
+    def _tc_transformer(self, layers, tws, h, pol):
         """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,
         fp32 accumulate, residual added in fp32 in the epilogue) and so does the attention (ops.attention_tc); LayerNorm is
         fp32 SIMT."""
         B, T, C = h.shape
         dev = h.device
-        xa = Act(B, T, C, dev, split=True)
-        fa = Act(B, T, 4 * C, dev, split=True)
+        xa = pol.act(B, T, C, dev)    # legacy bf16 / exact: (hi, lo) pairs; fp16: one plane
+        fa = pol.act(B, T, 4 * C, dev)
         qkv = torch.empty((B, T, 3 * C), device=dev, dtype=torch.float32)
         rope = self._rope_table(T, dev)
         for (ln, *_), (Wqkv, Wo, Wfc1, Wfc2) in zip(layers, tws):
@@ -258,20 +266,20 @@ class Mimi(Codec):
         B, T = sig.shape
         dev = sig.device
         C = self._enc[0].cout
-        smin = self.enc_split_min
-        x = Act(B, T, C, dev, split=C >= smin)
-        xe = Act(B, T, C, dev, split=C >= smin)
+        pol = self.pol_enc
+        x = pol.act(B, T, C, dev)
+        xe = pol.act(B, T, C, dev)
         ops.conv_first_bf16(self._enc[0], sig, y=x, y_act=xe, act=ACT_ELU)
         L = T
         for i, (Wk3, Wk1, Wdown, r) in enumerate(self._tenc):
             Lout = -(-L // r)
-            ye = Act(B, L, C, dev, hr=Lout * r - L, split=C >= smin)
-            self._tc_resblock(Wk3, Wk1, x, xe, ye, split_min=smin)
+            ye = pol.act(B, L, C, dev, hr=Lout * r - L)
+            self._tc_resblock(Wk3, Wk1, x, xe, ye, pol)
             ye.fill_halo(PAD_ZERO)
             C = 2 * C
             last = i == len(self._tenc) - 1
-            x = None if last else Act(B, Lout, C, dev, split=C >= smin)
-            xe = Act(B, Lout, C, dev, split=C >= smin)
+            x = None if last else pol.act(B, Lout, C, dev)
+            xe = pol.act(B, Lout, C, dev)
             # kernel 2r / stride r causal conv: 2 taps over the r-phase view, tap 0 = the previous view row (zero for row 0)
             tc.conv_tc(Wdown, [Src(ye, taps=2, shift=-1, phases=r, rows=Lout)], Lout, y=x, y_act=xe, act=ACT_ELU, name="down_tc")
             L = Lout
@@ -282,23 +290,23 @@ class Mimi(Codec):
     def _decoder_tc(self, z):
         B, N, C = z.shape
         dev = z.device
-        za = Act(B, N, C, dev, split=True)
+        pol = self.pol_dec
+        za = pol.act(B, N, C, dev)
         ops.f32_to_act(z.contiguous(), za)
         C = self._tdec_first.n_total
-        ye = Act(B, N, C, dev, split=True)
+        ye = pol.act(B, N, C, dev)
         tc.conv_tc(self._tdec_first, [Src(za, taps=7, shift=-6)], N, y_act=ye, act=ACT_ELU, name="conv_k7_tc")
         L = N
         for i, (Wtr, Wk3, Wk1, r) in enumerate(self._tdec):
             C = C // 2
             Lout = L * r
-            sp = C >= SPLIT_MIN_CH
-            x = Act(B, Lout, C, dev, split=sp)
-            xe = Act(B, Lout, C, dev, split=sp)
+            x = pol.act(B, Lout, C, dev)
+            xe = pol.act(B, Lout, C, dev)
             tc.conv_tc(Wtr, [Src(ye, taps=2, shift=-1)], L, y=x, y_act=xe, act=ACT_ELU, act_mod=C, out_rows=Lout, out_ch=C, name="convtr_tc")
             last = i == len(self._tdec) - 1   # the last layer reads 16-sample view rows: causal zero halo + pad to whole rows
             pl = self._dec[-1].taps - 1
-            ye = Act(B, Lout, C, dev, hl=pl if last else 0, hr=(-pl) % 16 if last else 0, split=sp)
-            self._tc_resblock(Wk3, Wk1, x, xe, ye)
+            ye = pol.act(B, Lout, C, dev, hl=pl if last else 0, hr=(-pl) % 16 if last else 0)
+            self._tc_resblock(Wk3, Wk1, x, xe, ye, pol)
             L = Lout
         ye.fill_halo(PAD_ZERO)
         return tc.conv_last_phased(self._tdec_last, ye)
@@ -326,16 +334,17 @@ class Mimi(Codec):
     def _embeddings(self, sig, want_act=False):
         """sig [B,T] -> [B,N,512] at 12.5 Hz (HF/mimi:1455-1488)."""
         if self.tensor_path:
-            h = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()))
+            pol = self.pol_enc
+            h = self._tc_transformer(self._enc_tr, self._tenc_tr, self._encoder_tc(sig.contiguous()), pol)
             # `downsample` (HF/mimi:1419-1431): k4 s2 causal conv, replicate padding 2 left (+1 right for an odd length), as a
             # 2-tap GEMM over the 2-phase view of the padded split-bf16 copy; fp32 out
             B, L, C = h.shape
             N = -(-L // 2)
-            ha = Act(B, L, C, h.device, hl=2, hr=2 * N - L, split=True)
+            ha = pol.act(B, L, C, h.device, hl=2, hr=2 * N - L)
             ops.f32_to_act(h, ha)
             ha.fill_halo(PAD_REPLICATE)
             emb = torch.empty((B, N, C), device=h.device, dtype=torch.float32)
-            ea = Act(B, N, C, h.device, split=True) if want_act else None   # split-bf16 copy for the quantizer's input_proj GEMMs
+            ea = pol.act(B, N, C, h.device) if want_act else None   # 16-bit copy for the quantizer's input_proj GEMMs
             tc.conv_tc(self._tdown, [Src(ha, taps=2, origin=-2, phases=2, rows=N + 1)], N, y32=emb, y=ea, name="downsample_tc")
             return (emb, ea) if want_act else emb
         else:
@@ -414,11 +423,11 @@ class Mimi(Codec):
             toks = toks.to(torch.int64).contiguous()
             dev = toks.device
             D = self.codebooks.shape[2]
-            sa = Act(B, N, D, dev, split=True)
+            sa = self.pol_dec.act(B, N, D, dev)
             ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks[:1], 1, sa, code_offset=0, err_flag=self._err)
             z = torch.empty((B, N, self._tq_out.n_total), device=dev, dtype=torch.float32)
             if K > 1:
-                aa = Act(B, N, D, dev, split=True)
+                aa = self.pol_dec.act(B, N, D, dev)
                 ops.rvq_decode_bf16(toks.view(B * N, K), self.codebooks[1:], K - 1, aa, code_offset=1, err_flag=self._err)
                 tc.conv_tc(self._tq_out, [Src(sa), Src(aa)], N, y32=z, name="rvq_out_proj_tc")
             else:
@@ -427,6 +436,6 @@ class Mimi(Codec):
             z = self._toks_to_qfeats(toks, length)
         z = ops.upsample_dw(z, self.up_w)
         if self.tensor_path:
-            return self._decoder_tc(self._tc_transformer(self._dec_tr, self._tdec_tr, z))
+            return self._decoder_tc(self._tc_transformer(self._dec_tr, self._tdec_tr, z, self.pol_dec))
         z = self._run_transformer(self._dec_tr, z)
         return self._seanet(self._dec, z)[:, :, 0]

@@ -192,9 +192,16 @@ def conv_first_bf16(spec, sig, y=None, y_act=None, act=ACT_NONE, vlen=None, pad_
         ctypes.c_void_p(y.lo_ptr(0)) if (y is not None and y.lo is not None) else None,
         ctypes.c_void_p(y_act.lo_ptr(0)) if (y_act is not None and y_act.lo is not None) else None,
         y.bstride if y is not None else 0, y_act.bstride if y_act is not None else 0, B, T, C, K, pad_left, spec.pad_mode,
-        reflect_len, act, _stream()), "ac_conv_first_bf16")
+        reflect_len, act, int(_same_f16(y, y_act)), _stream()), "ac_conv_first_bf16")
     if _PROFILER:
         _PROFILER.end("conv_first", t0, 2.0 * B * T * K * C, 4.0 * B * T + 2.0 * B * T * C * ((y is not None) + (y_act is not None)))
+
+
+def _same_f16(*acts):
+    """hi-plane format shared by the given tc.Act outputs of one launch"""
+    fm = {a.f16 for a in acts if a is not None}
+    assert len(fm) == 1, "the outputs of one launch share the hi-plane format"
+    return fm.pop()
 
 
 def conv_last_bf16(spec, x_act, epi=EPI_NONE, pad_left=None):
@@ -232,6 +239,8 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE,
     d.dbg = _ptr(dbg)
     assert w_hh_bf16.dtype in (torch.bfloat16, torch.float16) and w_hh_bf16.is_contiguous()
     d.operand_fp16 = int(w_hh_bf16.dtype == torch.float16)
+    d.out_fp16 = int(_same_f16(out, final))
+    d.skip_fp16 = int(skip is not None and skip.f16)
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
     if _PROFILER:
@@ -244,7 +253,8 @@ def add_act_bf16(a, b, out, act=ACT_NONE):
     vp = lambda v: ctypes.c_void_p(v) if v is not None else None
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_add_act_bf16(vp(a.row_ptr(0)), vp(a.lo_ptr(0)), vp(b.row_ptr(0)), vp(b.lo_ptr(0)), vp(out.row_ptr(0)),
-                                          vp(out.lo_ptr(0)), a.B, a.L * a.C, a.bstride, b.bstride, out.bstride, act, _stream()),
+                                          vp(out.lo_ptr(0)), a.B, a.L * a.C, a.bstride, b.bstride, out.bstride, act,
+                                          int(a.f16) | (int(b.f16) << 1) | (int(out.f16) << 2), _stream()),
                "ac_add_act_bf16")
     if _PROFILER:
         _PROFILER.end("add_act_bf16", t0, 0.0, 6.0 * a.B * a.L * a.C)
@@ -257,7 +267,7 @@ def f32_to_act(x, out):
     vp = lambda v: ctypes.c_void_p(v) if v is not None else None
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_f32_to_split_bf16(_ptr(x), vp(out.row_ptr(0)), vp(out.lo_ptr(0)), out.B, out.L * out.C, x.stride(0),
-                                               out.bstride, _stream()), "ac_f32_to_split_bf16")
+                                               out.bstride, int(out.f16), _stream()), "ac_f32_to_split_bf16")
     if _PROFILER:
         _PROFILER.end("f32_to_split_bf16", t0, 0.0, 6.0 * x.numel())
 
@@ -272,7 +282,7 @@ def rvq_decode_bf16(codes, codebooks, stages, out_act, code_offset=0, err_flag=N
     _lib.check(_lib.lib().ac_rvq_decode_bf16(_ptr(codes), _ptr(codebooks), ctypes.c_void_p(out_act.row_ptr(0)),
                                              ctypes.c_void_p(out_act.lo_ptr(0)) if out_act.lo is not None else None, rows, out_act.L,
                                              out_act.bstride, D, codebooks.shape[1], stages, codes.shape[-1], code_offset,
-                                             _ptr(err_flag), _stream()), "ac_rvq_decode_bf16")
+                                             _ptr(err_flag), int(out_act.f16), _stream()), "ac_rvq_decode_bf16")
     if _PROFILER:
         _PROFILER.end("rvq_decode", t0, 0.0, 8.0 * rows * stages + 4.0 * rows * D * stages + 2.0 * rows * D)
 
@@ -395,7 +405,7 @@ def layernorm_act(x, w, b, out, eps=1e-5):
     vp = lambda v: ctypes.c_void_p(v) if v is not None else None
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_layernorm_split_bf16(_ptr(x), _ptr(w), _ptr(b), vp(out.row_ptr(0)), vp(out.lo_ptr(0)), out.B, out.L, out.C,
-                                                  out.bstride, eps, _stream()), "ac_layernorm_split_bf16")
+                                                  out.bstride, eps, int(out.f16), _stream()), "ac_layernorm_split_bf16")
     if _PROFILER:
         _PROFILER.end("layernorm_split_kernel", t0, 0.0, 8.0 * x.numel())
 
@@ -426,7 +436,7 @@ def attention_tc(qkv, rope, heads, head_dim, window, out_act=None, out32=False):
         hi, lo, bs = out_act.row_ptr(0), out_act.lo_ptr(0), out_act.bstride
     t0 = _PROFILER.begin() if _PROFILER else None
     _lib.check(_lib.lib().ac_attention_tc(_ptr(qkv), _ptr(rope), _ptr(o32), vp(hi), vp(lo), bs, B, T, heads, head_dim, window,
-                                          1.0 / math.sqrt(head_dim), _stream()), "ac_attention_tc")
+                                          1.0 / math.sqrt(head_dim), int(out_act is not None and out_act.f16), _stream()), "ac_attention_tc")
     if _PROFILER:
         _PROFILER.end("attention_tc_kernel", t0, 4.0 * B * heads * head_dim * T * min(T, window) / 2, 4.0 * qkv.numel() + 4.0 * B * T * heads * head_dim)
     return o32

@@ -15,18 +15,28 @@ from . import _lib, ops
 from ._lib import AcConvTcDesc, AcResunitTcDesc
 
 
+FMT_A_F16, FMT_W_HIB, FMT_Y_F16, FMT_YACT_F16, FMT_RES_F16, FMT_W2_HIB = 1, 2, 4, 8, 16, 32  # AC_FMT_* of the C header
+
+
 class Act:
-    """channels-last bf16 activation with halo rows."""
+    """channels-last 16-bit activation with halo rows: a hi plane (bf16, or IEEE fp16 with f16=True) and an optional
+    lo plane bf16(x - float(hi))."""
 
-    __slots__ = ("buf", "lo", "hl", "hr", "L", "C")
+    __slots__ = ("buf", "lo", "hl", "hr", "L", "C", "f16")
 
-    def __init__(self, B, L, C, device, hl=0, hr=0, zero=False, split=False):
-        """split=True adds a lo plane (x - bf16(x), also bf16): the pair carries ~16 mantissa bits through
-        the bf16 tensor cores (A_hi*W + A_lo*W_hi)."""
+    def __init__(self, B, L, C, device, hl=0, hr=0, zero=False, split=False, f16=False):
+        """split=True adds the lo plane: (bf16, bf16) carries ~17 significant bits through the tensor cores
+        (A_hi*W_hi + A_hi*W_lo + A_lo*W_hi), (fp16, bf16) ~20.  f16=True alone (one fp16 plane, 11 bits, one product) is
+        already more accurate than the bf16 pair of products."""
         alloc = torch.zeros if zero else torch.empty
-        self.buf = alloc((B, hl + L + hr, C), device=device, dtype=torch.bfloat16)
+        self.buf = alloc((B, hl + L + hr, C), device=device, dtype=torch.float16 if f16 else torch.bfloat16)
         self.lo = alloc((B, hl + L + hr, C), device=device, dtype=torch.bfloat16) if split else None
-        self.hl, self.hr, self.L, self.C = hl, hr, L, C
+        self.hl, self.hr, self.L, self.C, self.f16 = hl, hr, L, C, bool(f16)
+
+    def value(self):
+        """fp32 value of the valid rows (hi + lo), for tests"""
+        v = self.buf[:, self.hl:self.hl + self.L].float()
+        return v if self.lo is None else v + self.lo[:, self.hl:self.hl + self.L].float()
 
     @property
     def B(self):
@@ -51,7 +61,7 @@ class Act:
         if self.lo is None:
             return self
         v = Act.__new__(Act)
-        v.buf, v.lo, v.hl, v.hr, v.L, v.C = self.buf, None, self.hl, self.hr, self.L, self.C
+        v.buf, v.lo, v.hl, v.hr, v.L, v.C, v.f16 = self.buf, None, self.hl, self.hr, self.L, self.C, self.f16
         return v
 
     def fill_halo(self, mode, reflect_len=0):
@@ -77,6 +87,49 @@ class Src:
         self.rows = rows if rows is not None else act.L
 
 
+class Policy:
+    """Operand formats of one half (encoder / decoder) of a codec on the tensor path.
+      f16            hi planes (activations and weights) are IEEE fp16 instead of bf16
+      act_split_min  activations with >= this many channels carry a bf16 lo plane
+      w_split        True / False: every weight matrix is / is not the (hi, lo) pair; None: decided per layer by the codec's
+                     W_SINGLE regex (the legacy error-compensated bf16 policy)
+      hib            f16 weights carry the extra bf16(W) plane that multiplies the activations' lo planes
+    The three precisions: "bf16" = (False, 128-ish, None, False) -- two to three bf16 products per MAC; "fp16" = (True, never,
+    False, False) -- ONE fp16 product per MAC, more accurate than the bf16 pair (11-bit operands) at half the tensor work;
+    "exact" encoder = (True, 0, True, True) -- three products, ~2^-20 operand precision: the reference's tokens."""
+
+    def __init__(self, f16, act_split_min, w_split, hib=False):
+        self.f16, self.act_split_min, self.w_split, self.hib = f16, act_split_min, w_split, hib
+
+    @property
+    def full(self):
+        return self.act_split_min == 0
+
+    def split(self, C):
+        return C >= self.act_split_min
+
+    def act(self, B, L, C, device, split=None, **kw):
+        return Act(B, L, C, device, split=self.split(C) if split is None else split, f16=self.f16, **kw)
+
+    def weights(self, w, bias, by_name=True, alpha=None):
+        split = by_name if self.w_split is None else self.w_split
+        return TcWeights(w, bias, alpha, split=split, f16=self.f16, hib=self.hib and self.f16)
+
+
+NEVER = 1 << 30
+
+
+def policies(precision, legacy_split_min=128, legacy_dec_split_min=None):
+    """(encoder policy, decoder policy) of a precision mode"""
+    if precision == "bf16":
+        return Policy(False, legacy_split_min, None), Policy(False, legacy_dec_split_min or legacy_split_min, None)
+    one = Policy(True, NEVER, False)
+    if precision == "fp16":
+        return one, one
+    assert precision == "exact"
+    return Policy(True, 0, True, True), one
+
+
 def pick_bk(*channels):
     for bk in (64, 32, 16):
         if all(c % bk == 0 for c in channels):
@@ -85,15 +138,25 @@ def pick_bk(*channels):
 
 
 class TcWeights:
-    """bf16 [n_total][k_total] + fp32 bias; `apply` supports module.to()."""
+    """16-bit weight planes [planes][n_total][k_total] + fp32 bias; `apply` supports module.to()."""
 
-    def __init__(self, w, bias, alpha=None, split=True):
-        """split: store W as the pair (W_hi, W_lo = bf16(W - W_hi)), stacked [2][n][k]; both tiles sit in shared memory
-        and every A tile is multiplied by both, so weight rounding error drops from 2^-9 to ~2^-17 at no HBM cost."""
+    def __init__(self, w, bias, alpha=None, split=True, f16=False, hib=False):
+        """split: store W as the pair (W_hi, W_lo = round(W - W_hi)); both tiles sit in shared memory and every A tile is
+        multiplied by both, so weight rounding error drops from 2^-9 to ~2^-17 (bf16) / 2^-12 to ~2^-21 (f16) at no HBM cost.
+        f16: the planes are IEEE fp16 (the A operands' hi planes must be fp16 too: both operands of one tcgen05.mma share the
+        format).  hib (f16 only): a third plane bf16(W) that the products of the A operands' bf16 lo planes multiply."""
         w = w.float()
-        hi = w.to(torch.bfloat16)
-        self.split = bool(split)
-        self.w = (torch.stack([hi, (w - hi.float()).to(torch.bfloat16)]) if split else hi).contiguous()
+        assert not hib or f16
+        if f16:
+            assert w.abs().max() < 6.0e4, "weights outside the fp16 range"
+            hi = w.to(torch.float16)
+            planes = [hi] + ([(w - hi.float()).to(torch.float16)] if split else [])
+            planes = [p.view(torch.int16) for p in planes] + ([w.to(torch.bfloat16).view(torch.int16)] if hib else [])
+            self.w = torch.stack(planes).contiguous()      # mixed 16-bit formats: kept as raw bit patterns
+        else:
+            hi = w.to(torch.bfloat16)
+            self.w = (torch.stack([hi, (w - hi.float()).to(torch.bfloat16)]) if split else hi).contiguous()
+        self.split, self.f16, self.hib = bool(split), bool(f16), bool(hib)
         self.bias = bias.float().contiguous() if bias is not None else None
         self.alpha = alpha.float().contiguous() if alpha is not None else None
         self.n_total, self.k_total = w.shape
@@ -150,6 +213,11 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
         assert y32.is_contiguous() and y32.dtype == torch.float32 and y32.shape[0] == B and y32[0].numel() == out_rows * out_ch
         d.y32, d.y32_bstride = y32.data_ptr(), y32.stride(0)
     d.act, d.epi, d.act_mod = act, epi, act_mod or out_ch
+    f16 = srcs[0].act.f16
+    assert all(s.act.f16 == f16 for s in srcs) and W.f16 == f16, "the A sources and the weights of one launch share the hi-plane format"
+    assert not (f16 and any(s.act.lo is not None for s in srcs)) or W.hib, "fp16 operands with a lo plane need TcWeights(hib=True)"
+    d.fmt = (FMT_A_F16 if f16 else 0) | (FMT_W_HIB if W.hib else 0) | (FMT_Y_F16 if (y is not None and y.f16) else 0) | \
+            (FMT_YACT_F16 if (y_act is not None and y_act.f16) else 0) | (FMT_RES_F16 if (res is not None and res.f16) else 0)
     d.batch, d.m_rows, d.n_tile_hint, d.grid_hint = B, m_rows, n_tile_hint, grid_hint
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_conv_tc(ctypes.byref(d), ops._stream()), "ac_conv_tc")
@@ -195,6 +263,13 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
         d.y, d.y_lo, d.y_bstride = y.row_ptr(0), y.lo_ptr(0), y.bstride
     if y_act is not None:
         d.y_act, d.y_act_lo, d.y_act_bstride = y_act.row_ptr(0), y_act.lo_ptr(0), y_act.bstride
+    f16 = A.f16
+    assert W1.f16 == f16 and W2.f16 == f16 and (x is None or x.f16 == f16), "one hi-plane format per launch"
+    assert not f16 or ((A.lo is None or W1.hib) and (not (h_split or (x is not None and x.lo is not None)) or W2.hib)), \
+        "fp16 operands with a lo plane need TcWeights(hib=True)"
+    d.fmt = (FMT_A_F16 if f16 else 0) | (FMT_W_HIB if W1.hib else 0) | (FMT_W2_HIB if W2.hib else 0) | \
+            (FMT_Y_F16 if (y is not None and y.f16) else 0) | (FMT_YACT_F16 if (y_act is not None and y_act.f16) else 0) | \
+            (FMT_RES_F16 if (res is not None and res.f16) else 0)
     d.batch, d.m_rows, d.bk, d.g_hint, d.grid_hint, d.dbl_hint = B, m_rows, bk or pick_bk(cin), g_hint, grid_hint, dbl_hint
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_resunit_tc(ctypes.byref(d), ops._stream()), "ac_resunit_tc")
@@ -268,7 +343,7 @@ def autotune(key, variants):
 LAST_PHASES = 16
 
 
-def last_conv_weights_phased(spec, split=True):
+def last_conv_weights_phased(spec, split=True, f16=False, hib=False):
     """Cout = 1 last layer as a stride-16 convolution with 16 output channels: GEMM row n produces the 16 consecutive samples
     16n .. 16n+15 from the two 16-sample view rows n, n+1 of the padded input (a Toeplitz weight matrix
     W[j][tau*C + c] = w[tau - j][c], 0 <= tau - j < taps).  16 useful accumulator columns per row instead of 1, and
@@ -280,7 +355,7 @@ def last_conv_weights_phased(spec, split=True):
     for j in range(P):
         w[j, j:j + taps] = spec.w[:, :, 0]
     bias = spec.bias.reshape(-1)[:1].float().repeat(P) if spec.bias is not None else None
-    return TcWeights(w.reshape(P, -1), bias, split=split)
+    return TcWeights(w.reshape(P, -1), bias, split=split, f16=f16, hib=hib)
 
 
 def last_conv_right_halo(T, hl):

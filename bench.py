@@ -8,7 +8,7 @@ over one batch of synthetic 10 s clips; workload = BASELINE.json configs[1]: EnC
 Prints ONE JSON line (rank 0).  Besides the contract's keys the line carries
   parity          tokens / waveform of the TIMED configuration against the unmodified reference wrappers run on the host
                   (near-ties, top-2 gap <= 1e-4, classified with the oracle's distances)
-  fast_mode       the same workload at precision="bf16" (fastest tensor path), with its own parity numbers
+  fast_mode       the same workload at precision="fp16" (one fp16 product per MAC: fastest tensor path), with its own parity
   extra_configs   the other BASELINE.json configs (DAC-44.1k 64 x 10 s, Mimi 128 x 10 s, EnCodec K=32), each with value /
                   roofline / parity, so that the driver's 1- and 8-GPU runs carry them
   gpu_eager_baseline  the reference wrappers moved to the same GPU with .to("cuda") (eager PyTorch: the reference's own GPU path)
@@ -404,8 +404,8 @@ def run_ours(args, rank, world, local_rank):
     if args.no_extras:
         return out
     # ---- the fastest tensor path on the same workload
-    if args.precision != "bf16":
-        fast, st = measure(ctx, args.codec, "bf16", args.steps, args.warmup, args.batch, with_e2e=False)
+    if args.precision != "fp16":
+        fast, st = measure(ctx, args.codec, "fp16", args.steps, args.warmup, args.batch, with_e2e=False)
         out["fast_mode"] = {k: fast[k] for k in ("value", "unit", "ms_per_step", "precision")}
         out["fast_mode"]["roofline_frac"] = fast["roofline"]["frac"]
         if cpu_legs:
@@ -495,8 +495,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU clips (default: the BASELINE workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (parity, cpu_baseline, gpu_eager_baseline)")
     ap.add_argument("--no-extras", action="store_true", help="skip fast_mode and extra_configs")
-    ap.add_argument("--precision", default="exact", choices=["exact", "bf16", "fp32"],
-                    help="exact (default): tensor path whose tokens equal the reference's; bf16: fastest tensor path")
+    ap.add_argument("--precision", default="exact", choices=["exact", "fp16", "bf16", "fp32"],
+                    help="exact (default): tensor path whose tokens equal the reference's; fp16: fastest tensor path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AC_ABI_VERSION 2
+#define AC_ABI_VERSION 3
 #define AC_API __attribute__((visibility("default")))
 
 /* padding modes of the input row index */
@@ -109,6 +109,7 @@ typedef struct ac_lstm_tc_desc {
     void* dbg;                 /* optional int64 [steps][8] clock samples (profiling aid), else NULL */
     int32_t operand_fp16;      /* 1: w_hh_bf16 holds IEEE fp16 and h[t-1] is fed back as fp16 (11-bit mantissas: |W_hh| and |h| < 1
                                   sit well inside the fp16 range) -- one product at 2^-12 instead of 2^-9 operand rounding */
+    int32_t out_fp16, skip_fp16; /* hi planes of out / final, and of skip, hold fp16 instead of bf16 (lo planes: bf16) */
 } ac_lstm_tc_desc;
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
 
@@ -152,7 +153,7 @@ AC_API int ac_rvq_decode_f32(const int64_t* codes, const float* codebooks, float
  * out_bf16[b*bstride + r*dim] (rows_per_clip rows per clip). */
 AC_API int ac_rvq_decode_bf16(const int64_t* codes, const float* codebooks, void* out_bf16, void* out_lo, int64_t rows,
                       int32_t rows_per_clip, int64_t bstride, int32_t dim, int32_t n_codes, int32_t stages,
-                      int32_t code_stride, int32_t code_offset, int32_t* err_flag, void* stream);
+                      int32_t code_stride, int32_t code_offset, int32_t* err_flag, int32_t out_f16, void* stream);
 
 /*
  * Polyphase windowed-sinc resampler (torchaudio.functional.resample, TA:1405-1432):
@@ -182,6 +183,16 @@ AC_API int ac_resample_f32(const float* x, const float* taps, float* y, int32_t 
  * applied once, at production time.  W is bf16 [n_total][k_total], columns ordered source, tap, k.
  * Replaces the same reference code as ac_conv1d_f32 (HF/encodec:82-282, HF/mimi:214-451, HF/dac:173-262,405-472).
  */
+/* operand / output formats of the tensor-path launches (`fmt` of ac_conv_tc_desc / ac_resunit_tc_desc).  The hi plane of an
+ * activation or weight is bf16 or IEEE fp16 (11 significant bits: one fp16 product is more accurate than the bf16 pair of
+ * products, at half the tensor work; values beyond +-65504 saturate); lo planes are always bf16(v - float(hi)). */
+#define AC_FMT_A_F16 1     /* hi planes of every A source (and of the hidden tile) and the W_hi / W_lo planes are fp16 */
+#define AC_FMT_W_HIB 2     /* with A_F16: an extra bf16(W) plane follows W_hi [W_lo]; the A_lo (bf16) products multiply it */
+#define AC_FMT_Y_F16 4     /* y hi plane is written as fp16 */
+#define AC_FMT_YACT_F16 8  /* y_act hi plane is written as fp16 */
+#define AC_FMT_RES_F16 16  /* res hi plane holds fp16 */
+#define AC_FMT_W2_HIB 32   /* ac_resunit_tc: the same as W_HIB for W2 (W_HIB then refers to W1) */
+
 typedef struct ac_tc_src {
     const void* base;            /* bf16: view row 0, phase 0, channel 0 of clip 0 */
     int32_t c0, phases, rows;    /* channels per phase, phases per view row, view rows per clip */
@@ -213,6 +224,7 @@ typedef struct ac_conv_tc_desc {
     const void* res_lo;          /* optional lo plane of `res` */
     const float* res32;          /* optional fp32 residual in the output's flat layout (clip stride res_bstride) */
     int32_t g_hint;              /* 128-row sub-tiles per tile (1, 2 or 4) sharing one A block and one W block; 0 = automatic */
+    int32_t fmt;                 /* AC_FMT_* flags; 0 = everything bf16 */
 } ac_conv_tc_desc;
 
 AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);
@@ -256,6 +268,7 @@ typedef struct ac_resunit_tc_desc {
     int32_t act0, e_split, x_from_a;
     const float* alpha0;
     int32_t x_row_off;                     /* x_from_a: view row (m + shift + x_row_off) holds raw x[m]; 0 <= x_row_off <= (taps-1)*dilation */
+    int32_t fmt;                           /* AC_FMT_* flags; 0 = everything bf16 (raw mode, act0 != NONE, is bf16 only) */
 } ac_resunit_tc_desc;
 
 AC_API int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream);
@@ -275,12 +288,12 @@ AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch,
  */
 AC_API int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* out_hi, void* out_lo,
                            int32_t batch, int64_t per_clip, int64_t a_bstride, int64_t b_bstride, int64_t out_bstride,
-                           int32_t act, void* stream);
+                           int32_t act, int32_t fmt /* bit 0: a_hi is fp16, bit 1: b_hi, bit 2: out_hi (else bf16) */, void* stream);
 
 /* fp32 [batch][per_clip] -> split-bf16 planes hi = bf16(x), lo = bf16(x - hi) (lo optional): the quantised latents
  * (RVQ decode output, fp32) entering the tensor-core decoder. */
 AC_API int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, int32_t batch, int64_t per_clip, int64_t x_bstride,
-                                int64_t out_bstride, void* stream);
+                                int64_t out_bstride, int32_t out_f16 /* hi plane as fp16 instead of bf16 */, void* stream);
 
 /*
  * Edge layers of the bf16 pipeline (HBM-bound, SIMT):
@@ -296,7 +309,7 @@ AC_API int ac_f32_to_split_bf16(const float* x, void* out_hi, void* out_lo, int3
 AC_API int ac_conv_first_bf16(const float* x, const float* w, const float* bias, const float* alpha, const int32_t* vlen,
                               void* y, void* y_act, void* y_lo, void* y_act_lo, int64_t y_bstride, int64_t y_act_bstride,
                               int32_t batch, int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode,
-                              int32_t reflect_len, int32_t act, void* stream);
+                              int32_t reflect_len, int32_t act, int32_t out_f16, void* stream);
 AC_API int ac_conv_last_bf16(const void* x, const float* w, const float* bias, float* y, int64_t x_bstride, int32_t batch,
                              int32_t T, int32_t C, int32_t K, int32_t pad_left, int32_t pad_mode, int32_t reflect_len,
                              int32_t epi, void* stream);
@@ -322,10 +335,11 @@ AC_API int ac_upsample_dw_f32(const float* x, const float* w, float* y, int32_t 
  */
 /* LayerNorm (as ac_layernorm_f32) written straight into split-bf16 planes [B] x out_bstride + [rows_per_clip][C]. */
 AC_API int ac_layernorm_split_bf16(const float* x, const float* w, const float* b, void* out_hi, void* out_lo, int32_t batch,
-                                   int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, void* stream);
+                                   int32_t rows_per_clip, int32_t C, int64_t out_bstride, float eps, int32_t out_f16, void* stream);
 AC_API int ac_rope_table_f32(const float* inv_freq, float* table, int32_t T, int32_t half, void* stream);
 AC_API int ac_attention_tc(const float* qkv, const float* rope, float* out32, void* out_hi, void* out_lo, int64_t out_bstride,
-                           int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, void* stream);
+                           int32_t batch, int32_t T, int32_t heads, int32_t head_dim, int32_t window, float scaling, int32_t out_f16,
+                           void* stream);
 
 /*
  * DAC residual VQ (hidden 1024, codebook dim 8), all stages fused, fp32.

@@ -1,5 +1,5 @@
 """Per-launch device times of one full-size step (CUDA events around every C-ABI launch), with the algorithmic
-GB/s and TFLOP/s of each launch.  Usage: [AC_PRECISION=exact|bf16] [AC_TUNE_FUSION=1] python scripts/layer_times.py
+GB/s and TFLOP/s of each launch.  Usage: [AC_PRECISION=exact|fp16|bf16] [AC_TUNE_FUSION=1] python scripts/layer_times.py
 [encodec|dac|mimi] [batch] [seconds]      (AC_TUNE_FUSION=1: let the tuner time fused against unfused blocks and print it)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(L, n), n
-    assert _lib.lib().ac_abi_version() == 2
+    assert _lib.lib().ac_abi_version() == 3
 
 
 def test_struct_mirror_matches_header_size():

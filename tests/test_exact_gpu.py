@@ -85,7 +85,7 @@ def _full_size(codec, ref_mod, sd, dev, B, T, K, pick, floors):
     return toks
 
 
-@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.995)), ("bf16", (0.93, 0.93))])
+@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.995)), ("fp16", (0.975, 0.975)), ("bf16", (0.93, 0.93))])
 def test_encodec_full_batch_vs_oracle(encodec_sd, dev, precision, floors):
     """BASELINE configs[1]: 64 x 10 s, K = 8.  exact: tokens equal the oracle's away from near-ties; bf16 (measured 0.951
     all / 0.952 safe): bounded within two points."""
@@ -101,7 +101,7 @@ def test_encodec_full_batch_vs_oracle(encodec_sd, dev, precision, floors):
         assert torch.equal(one[0], toks[17])
 
 
-@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.995)), ("bf16", (0.975, 0.975))])
+@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.995)), ("fp16", (0.99, 0.99)), ("bf16", (0.975, 0.975))])
 def test_dac_full_batch_vs_oracle(dac_sd, dev, precision, floors):
     """BASELINE configs[2]: 64 x 10 s at 44.1 kHz, K = 9 (oracle on one clip: ~15 s of CPU)."""
     import audiocodecs_b200 as A
@@ -113,7 +113,7 @@ def test_dac_full_batch_vs_oracle(dac_sd, dev, precision, floors):
         assert torch.equal(one[0], toks[41]), "tokens depend on the batch"
 
 
-@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.98)), ("bf16", (0.975, 0.97))])
+@pytest.mark.parametrize("precision,floors", [("exact", (0.999, 0.98)), ("fp16", (0.985, 0.975)), ("bf16", (0.975, 0.97))])
 def test_mimi_full_batch_vs_oracle(mimi_sd, dev, precision, floors):
     """BASELINE configs[3]: 128 x 10 s, K = 8 (1.3 % of Mimi's decisions are near-ties below 1e-4 on these weights)."""
     import audiocodecs_b200 as A
@@ -168,7 +168,7 @@ def test_device_guard_and_token_checks(encodec_sd, dev):
         assert torch.equal(t[0], ok[0])  # the clean clip of the batch is untouched
 
 
-@pytest.mark.parametrize("precision", ["exact", "fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["exact", "fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("case", range(3))
 def test_dac_odd_stride_golden(dev, case, precision):
     """The reference's DEFAULT DAC (`DAC(sample_rate)`: orig_sample_rate=16000) and the 24 kHz model: stride-5 strided /
@@ -191,7 +191,7 @@ def test_dac_odd_stride_golden(dev, case, precision):
     eq = toks.cpu() == ref_toks
     safe = ~c["near_tie"]
     print(f"{c['name']} {precision}: tokens equal {eq.float().mean().item():.5f}, away from near-ties {eq[safe].float().mean().item():.5f}")
-    if precision != "bf16":
+    if precision in ("exact", "fp32"):
         assert eq[safe].all(), f"{int((~eq[safe]).sum())} code mismatches away from near-ties"
     else:
         assert eq[safe].float().mean().item() > 0.95
