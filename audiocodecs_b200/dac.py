@@ -258,8 +258,10 @@ class DAC(Codec):
 
     # ------------------------------------------------------------------ bf16 tensor path: execution
     def _split_res(self, pol, C):
-        """the raw residual stream (touched by epilogues only, never an MMA operand): lo plane from 64 channels up"""
-        return pol.full or C >= self.split_res_min_ch
+        """the raw residual stream (touched by epilogues only, never an MMA operand): with bf16 hi planes it needs the lo
+        plane from 64 channels up (8 bits per skip-add is not enough); one fp16 plane (11 bits) is, so "fp16" carries none
+        (a third less traffic in the unit kernels); "exact" always carries it"""
+        return pol.full or (not pol.f16 and C >= self.split_res_min_ch)
 
     def _tc_run_units(self, units, x, xs, next_alpha, out_halo=(0, 0), enc=False):
         pol = self.pol_enc if enc else self.pol_dec
@@ -293,7 +295,7 @@ class DAC(Codec):
             if 2 * C <= 512:
                 fv = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)]
                 variants = fv if enc else fv + variants
-            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc, xs.f16), variants)
+            tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc, xs.f16, W7.planes, W1.planes), variants)
             x, xs = y, ys
         return xs
 

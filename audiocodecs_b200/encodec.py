@@ -259,7 +259,7 @@ class Encodec(Codec):
                 return lambda: tc.resunit_tc(Wk3, Wtail, a, L, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, act0=ACT_ELU,
                                              e_split=x.lo is not None, x_from_a=True, g_hint=g, dbl_hint=dbl, name="resblock_tc")
 
-            tc.autotune(("encodec_resblock_raw", B, L, C), [(f"raw_g{g}_d{dbl}", raw(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)])
+            tc.autotune(("encodec_resblock_raw", B, L, C, x.lo is not None, Wk3.planes, Wtail.planes), [(f"raw_g{g}_d{dbl}", raw(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)])
             return
         xe.fill_halo(PAD_REFLECT, 3 if L <= 2 else 0)
         a = Src(xe, taps=3, origin=-2, rows=L + 2)
@@ -278,7 +278,7 @@ class Encodec(Codec):
             variants.append(("unfused", unfused))
         elif C > FUSED_MAX_CH:
             variants = [("unfused", unfused)]
-        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None, hs, x.f16), variants)
+        tc.autotune(("encodec_resblock", B, L, C, x.lo is not None, hs, x.f16, Wk3.planes, Wtail.planes), variants)
 
     def _encoder_tc(self, sig, vlen=None):
         B, T = sig.shape

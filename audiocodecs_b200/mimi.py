@@ -234,7 +234,7 @@ class Mimi(Codec):
         variants = [("unfused", unfused)]
         if C <= 256:
             variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
-        tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs, x.f16), variants)
+        tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs, x.f16, Wk3.planes, Wk1.planes), variants)
 
     def _tc_transformer(self, layers, tws, h, pol):
         """fp32 residual stream h [B,T,512]; the four projections of every layer run on tcgen05 (split-bf16 operands,

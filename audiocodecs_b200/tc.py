@@ -161,6 +161,11 @@ class TcWeights:
         self.alpha = alpha.float().contiguous() if alpha is not None else None
         self.n_total, self.k_total = w.shape
 
+    @property
+    def planes(self):
+        """weight planes held in shared memory per block: decides which tilings fit, so it belongs in every tuning key"""
+        return 1 + int(self.split) + int(self.hib)
+
     def apply(self, fn):
         self.w = fn(self.w)
         self.bias = fn(self.bias) if self.bias is not None else None

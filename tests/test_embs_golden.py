@@ -1,7 +1,7 @@
 """`embs()` of the three wrappers against summaries recorded from the LIVE reference wrappers (oracle/make_golden_embs.py:
 shape, fp64 checksum, 64 sampled entries per configuration).  The configurations whose `embs()` is pure tensor algebra run
-on the CPU; Mimi's projected embeddings (latent=False, golden key `mimi_k3_latent0`) go through the conv kernels: a GPU test
-for them belongs to the next round (no GPU time was left to run it in this one)."""
+on the CPU; Mimi's projected embeddings (latent=False, golden key `mimi_k3_latent0`) go through the conv kernels and are
+checked on the GPU (tests/test_feats_gpu.py)."""
 import os
 
 import pytest

@@ -44,7 +44,7 @@ def _to_dev(W):
     return W
 
 
-@pytest.mark.parametrize("pol,tol", [(ONE, 1.5e-3), (FULL, 3e-6), (BF, 3e-5)])
+@pytest.mark.parametrize("pol,tol", [(ONE, 1.5e-3), (FULL, 6e-6), (BF, 3e-5)])
 @pytest.mark.parametrize("B,L,Cin,Cout,K,dil", [(2, 300, 64, 64, 1, 1), (1, 200, 32, 16, 3, 1), (2, 150, 128, 256, 7, 3), (1, 130, 16, 32, 3, 1)])
 def test_conv_tc_formats(pol, tol, B, L, Cin, Cout, K, dil):
     """K-tap conv (zero padding through TMA out-of-bounds fill), fp32 output + ELU'd 16-bit output in the policy's format."""
