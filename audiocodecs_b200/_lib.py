@@ -45,7 +45,7 @@ class AcConvTcDesc(ctypes.Structure):
                 ("y_bstride", c_i64), ("y_act_bstride", c_i64), ("y32_bstride", c_i64), ("res_bstride", c_i64),
                 ("out_shift", c_i64), ("out_valid", c_i64),
                 ("batch", c_i32), ("m_rows", c_i32), ("n_tile_hint", c_i32), ("grid_hint", c_i32),
-                ("res_lo", c_vp), ("res32", c_vp), ("g_hint", c_i32), ("fmt", c_i32)]
+                ("res_lo", c_vp), ("res32", c_vp), ("g_hint", c_i32), ("fmt", c_i32), ("flush_adds", c_i32)]
 
 
 class AcResunitTcDesc(ctypes.Structure):

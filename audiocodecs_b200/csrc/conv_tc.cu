@@ -22,6 +22,13 @@
 // warp 2 = W producer, warps 3-18 = epilogue (tcgen05.ld -> bias, residual, raw / activated / lo-plane bf16
 // or fp32 stores; the activation written is the CONSUMER's, so no layer re-reads a tensor just to activate it).
 // TMEM holds up to two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Chunked accumulation (flush_adds > 0, the "exact" encoder): the tcgen05 fp32 accumulator TRUNCATES every add (measured,
+// scripts/accum_probe.py: the error of a K-deep contraction is a shrink of ~2e-8 per tcgen05.mma into the accumulator -- 2e-5
+// at K = 4096 with three products, whatever the operand precision).  So a tile's contraction is cut into partial sums of a
+// few dozen MMAs each: the two accumulator stages alternate as PARTIAL accumulators, and the epilogue warps add every
+// finished partial into a running sum kept in a third TMEM region with round-to-nearest fp32 adds (tcgen05.ld / add /
+// tcgen05.st by the thread that owns those lanes and columns).  The error per layer then no longer grows with K.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -80,6 +87,8 @@ struct TcParams {
     __nv_bfloat16* y_lo;          // optional lo planes: lo = bf16(v - float(bf16(v)))
     __nv_bfloat16* y_act_lo;
     float* y32;
+    int flush_blocks, n_partials; // chunked accumulation: a partial sum per `flush_blocks` (chunk, tap) blocks; n_partials per tile (1 = off)
+    uint32_t run_col;             // TMEM column of the running sums (after the two partial stages)
     int w_rows;                   // rows of one weight plane in the W tensor map (n_total); W_lo starts at row w_rows
     int act, epi, act_mod;
     int wide_ok;                  // every output/residual row run of 16 columns is 32-byte aligned: 256-bit stores
@@ -120,12 +129,39 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
             rnext[0] = r[0]; rnext[1] = r[1]; rnext[2] = r[2]; rnext[3] = r[3];
         }
     };
-    int it = 0;
+    int it = 0;  // accumulator hand-overs so far (= tiles, or partial sums with chunked accumulation)
+    const uint32_t run_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + p.run_col;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int mg = rest % p.m_groups;
         const int b = rest / p.m_groups;
+        // chunked accumulation: fold every partial but the last into the running sums (this thread's own lanes / columns:
+        // the items of a warp are the same for every partial, so no other warp ever touches these TMEM cells)
+        for (int q = 0; q + 1 < p.n_partials; ++q, ++it) {
+            const int pas = it & 1;
+            mbar_wait(&tfull[pas], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t paddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + pas * p.G * p.n_tile;
+            for (int item = slot; item < items; item += EPI_WARPS / 4) {
+                uint32_t v[16];
+                tmem_ld16(paddr + item * 16, v);
+                if (q > 0) {
+                    uint32_t r[16];
+                    tmem_ld16(run_addr + item * 16, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(r[i]));
+                } else {
+                    tmem_ld_wait();
+                }
+                tmem_st16(run_addr + item * 16, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[pas]);
+        }
         const int as = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
         int g = 0, c = slot;
@@ -137,6 +173,13 @@ __device__ __forceinline__ void epilogue(const TcParams& p, uint32_t tmem_base, 
         for (int item = slot; item < items; item += EPI_WARPS / 4) {
             uint32_t v[16];
             tmem_ld16(taddr + g * p.n_tile + c * 16, v);
+            if (p.n_partials > 1) {  // last partial + running sums (item * 16 == g * n_tile + c * 16)
+                uint32_t r[16];
+                tmem_ld16(run_addr + g * p.n_tile + c * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(r[i]));
+            }
             const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
             const int n0 = nt * p.n_tile + c * 16;
             const long long flat = (long long)m * p.n_total + n0 - p.out_shift;
@@ -308,14 +351,15 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uin
     const uint64_t desc_base = make_smem_desc(0, row_bytes);  // everything but the start address
     const uint32_t a_ring_u = smem_u32(a_ring), w_area_u = smem_u32(w_area);
     if (p.w_resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
-    int it = 0;
+    int it = 0;  // accumulator hand-overs so far (= tiles, or partial sums with chunked accumulation)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = p.acc_stages == 2 ? (it & 1) : 0;
-        const uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+        int as = p.acc_stages == 2 ? (it & 1) : 0;
+        uint32_t tphase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tempty[as], tphase ^ 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + as * p.G * p.n_tile;
+        uint32_t d_base = tmem_base + as * p.G * p.n_tile;
         uint32_t acc = 0;  // first MMA into each accumulator overwrites
+        int blk = 0;       // (chunk, tap) blocks issued into the current partial sum
         for (int s = 0; s < p.n_src; ++s) {
             const TcSrc& S = p.src[s];
             const int taps = S.taps, chunks = S.chunks, has_lo = S.has_lo;
@@ -325,6 +369,20 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* a_ring, uin
                 tc_fence_after();
                 const uint32_t a_hi = a_ring_u + astage * p.a_stage_bytes;
                 for (int j = 0; j < taps; ++j) {
+                    if (p.flush_blocks && blk == p.flush_blocks) {
+                        // chunked accumulation: hand this partial sum to the epilogue warps, continue in the other stage
+                        if (leader) umma_commit(&tfull[as]);
+                        __syncwarp();
+                        ++it;
+                        as = it & 1;
+                        tphase = (it >> 1) & 1;
+                        mbar_wait(&tempty[as], tphase ^ 1);
+                        tc_fence_after();
+                        d_base = tmem_base + as * p.G * p.n_tile;
+                        acc = 0;
+                        blk = 0;
+                    }
+                    ++blk;
                     uint32_t w_hi, w_lo, w_hib;
                     if (p.w_resident) {
                         w_hi = w_area_u + (S.kb0 + j * chunks + cc) * p.w_kb_bytes;
@@ -565,6 +623,13 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
         if ((w_planes == 1 || c <= 128) && d->n_total % c == 0) { n_tile = c; break; }
     if (d->n_total % n_tile != 0) n_tile = d->n_total >= 128 ? 128 : 16;
     if (d->n_tile_hint > 0) n_tile = d->n_tile_hint;
+    // chunked accumulation: the two accumulator stages become partial sums and a third region holds the running sums, so
+    // 3 * G * n_tile TMEM columns are needed
+    int n_blocks = 0;
+    for (int s = 0; s < d->n_src; ++s)
+        if (d->src[s].lo_of < 0) n_blocks += d->src[s].taps * (d->src[s].c0 * d->src[s].phases);  // contraction length, for now
+    const bool want_flush = d->flush_adds > 0 && 2 * (n_blocks / 16) * (1 + w_split + 1) > 3 * d->flush_adds;  // > 1.5 partials' worth
+    if (want_flush && n_tile > 128 && d->n_tile_hint <= 0) n_tile = d->n_total % 128 == 0 ? 128 : (d->n_total % 96 == 0 ? 96 : (d->n_total % 64 == 0 ? 64 : n_tile));
     AC_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "ac_conv_tc: n_tile %d", n_tile);
     const int n_tiles = (d->n_total + n_tile - 1) / n_tile;
 
@@ -611,7 +676,7 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
                     if (G * n_tile * 2 > 512) continue;                                   // keep two accumulator stages when grouping
                     if ((m_tiles / G) * n_tiles * d->batch < 2LL * sms) continue;         // not enough tiles to fill the chip
                 }
-                if (G * n_tile > 512) continue;
+                if (G * n_tile > 512 || (want_flush && 3 * G * n_tile > 512)) continue;
                 uint32_t a_plane = 0;  // A stage: the largest block over sources
                 for (int s = 0; s < n_ms; ++s) {
                     const int R = G * TILE_M + (ms[s].hi->taps - 1) * ms[s].hi->dilation;
@@ -667,8 +732,22 @@ extern "C" int ac_conv_tc(const ac_conv_tc_desc* d, void* stream) {
     p.w_split = w_split; p.f16 = f16; p.w_hib = w_hib;
     p.y_f16 = (d->fmt & AC_FMT_Y_F16) ? 1 : 0; p.ya_f16 = (d->fmt & AC_FMT_YACT_F16) ? 1 : 0; p.res_f16 = (d->fmt & AC_FMT_RES_F16) ? 1 : 0;
     p.acc_stages = 2 * p.G * n_tile <= 512 ? 2 : 1;
+    p.flush_blocks = 0; p.n_partials = 1; p.run_col = 0;
+    if (want_flush && 3 * p.G * n_tile <= 512) {
+        int blocks = 0;  // (chunk, tap) blocks per tile, each bk/16 k-steps x products MMAs per sub-tile
+        for (int s = 0; s < n_ms; ++s) blocks += ms[s].hi->taps * (ms[s].hi->c0 * ms[s].hi->phases / p.bk);
+        const int per_block = (p.bk / 16) * (1 + w_split + (any_lo ? 1 : 0));
+        int fb = d->flush_adds / per_block;
+        if (fb < 1) fb = 1;
+        if (blocks > fb) {
+            p.flush_blocks = fb;
+            p.n_partials = (blocks + fb - 1) / fb;
+            p.run_col = 2u * p.G * n_tile;
+            p.acc_stages = 2;
+        }
+    }
     uint32_t cols = 32;
-    while (cols < (uint32_t)(p.acc_stages * p.G * n_tile)) cols <<= 1;
+    while (cols < (uint32_t)((p.acc_stages + (p.n_partials > 1 ? 1 : 0)) * p.G * n_tile)) cols <<= 1;
     p.tmem_cols = cols;
 
     TcMaps maps;

@@ -318,6 +318,25 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
 
 }  // namespace
 
+// Diagnostic: how many clusters of `cluster_size` CTAs of this kernel the device can hold at once (cudaOccupancyMaxActiveClusters).
+extern "C" int ac_lstm_tc_max_clusters(int32_t cluster_size, int32_t smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) { ac::set_error("ac_lstm_tc_max_clusters: %s", cudaGetErrorString(e)); return -1; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cluster_size * 16);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, (const void*)lstm_tc_kernel, &cfg);
+    if (e != cudaSuccess) { ac::set_error("ac_lstm_tc_max_clusters: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+    return n;
+}
+
 extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     AC_REQUIRE(d && d->pre && d->w_hh_bf16, "ac_lstm_tc: null pointer");
     AC_REQUIRE(d->hidden == HID, "ac_lstm_tc: hidden %d (this kernel is built for %d)", d->hidden, HID);

@@ -220,6 +220,9 @@ def conv_last_bf16(spec, x_act, epi=EPI_NONE, pad_left=None):
     return out
 
 
+LSTM_SIDE_STREAM = {}  # current stream id -> high-priority stream the recurrence kernels of that stream run on (overlap mode)
+
+
 def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE, dbg=None):
     """tensor-core LSTM recurrence: pre [B,T,2048] fp32; out / skip / final are tc.Act (bf16 hi[/lo] planes).
     w_hh_bf16: [2048,512] bf16, or fp16 (then h is fed back as fp16 too: 11-bit operands)."""
@@ -242,7 +245,23 @@ def lstm_tc(pre, w_hh_bf16, out=None, skip=None, final=None, final_act=ACT_NONE,
     d.out_fp16 = int(_same_f16(out, final))
     d.skip_fp16 = int(skip is not None and skip.f16)
     t0 = _PROFILER.begin() if _PROFILER else None
-    _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
+    cur = torch.cuda.current_stream()
+    side = LSTM_SIDE_STREAM.get(cur.cuda_stream)
+    if side is not None:
+        # the cluster kernel goes to a high-priority stream: when SMs free up at a kernel boundary of the (capped) tap-GEMM
+        # kernels its 16-CTA clusters are placed first, and the GEMMs of the other half-batch run beside it
+        side.wait_stream(cur)
+        _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), ctypes.c_void_p(side.cuda_stream)), "ac_lstm_tc")
+        cur.wait_stream(side)
+        for t in (pre, w_hh_bf16):
+            t.record_stream(side)
+        for a in (out, skip, final):
+            if a is not None:
+                a.buf.record_stream(side)
+                if a.lo is not None:
+                    a.lo.record_stream(side)
+    else:
+        _lib.check(_lib.lib().ac_lstm_tc(ctypes.byref(d), _stream()), "ac_lstm_tc")
     if _PROFILER:
         _PROFILER.end("lstm_tc_kernel", t0, 2.0 * B * T * C4 * (C4 // 4), 4.0 * pre.numel() + 2.0 * B * T * (C4 // 4))
 

@@ -15,6 +15,13 @@ from . import _lib, ops
 from ._lib import AcConvTcDesc, AcResunitTcDesc
 
 
+FLUSH_ADDS = 96  # "exact" launches: tcgen05.mma per partial sum of the chunked accumulation (see csrc/conv_tc.cu); 0 = off.
+                 # Measured on the EnCodec encoder (scripts/encoder_error_probe.py): embedding error 3.1e-5 with one accumulator
+                 # per tile, 6.9e-6 at 24 (+1.2 ms per step: grouped tiles no longer fit tensor memory), about the same at 96
+                 # (+0.3 ms) -- below that the fp16 recurrence of the LSTM (5e-6) dominates
+GRID_CAP = 0  # > 0: persistent tap-GEMM kernels launch at most this many CTAs (leaves SMs to a concurrently running LSTM cluster
+              # kernel of another stream -- audiocodecs_b200.overlap); 0 = one CTA per SM
+
 FMT_A_F16, FMT_W_HIB, FMT_Y_F16, FMT_YACT_F16, FMT_RES_F16, FMT_W2_HIB = 1, 2, 4, 8, 16, 32  # AC_FMT_* of the C header
 
 
@@ -175,7 +182,7 @@ class TcWeights:
 def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32: torch.Tensor = None, res: Act = None,
             res32: torch.Tensor = None,
             act=ops.ACT_NONE, epi=ops.EPI_NONE, alpha=None, act_mod=0, out_rows=None, out_ch=None, out_shift=0, bk=None,
-            n_tile_hint=0, grid_hint=0, name="conv_tc"):
+            n_tile_hint=0, grid_hint=0, flush_adds=0, name="conv_tc"):
     """Launch one tap-GEMM.  Outputs are Acts (bf16, flat layout starting at their valid row 0) and/or a
     contiguous fp32 tensor [B, out_rows, out_ch]."""
     d = AcConvTcDesc()
@@ -223,7 +230,8 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
     assert not (f16 and any(s.act.lo is not None for s in srcs)) or W.hib, "fp16 operands with a lo plane need TcWeights(hib=True)"
     d.fmt = (FMT_A_F16 if f16 else 0) | (FMT_W_HIB if W.hib else 0) | (FMT_Y_F16 if (y is not None and y.f16) else 0) | \
             (FMT_YACT_F16 if (y_act is not None and y_act.f16) else 0) | (FMT_RES_F16 if (res is not None and res.f16) else 0)
-    d.batch, d.m_rows, d.n_tile_hint, d.grid_hint = B, m_rows, n_tile_hint, grid_hint
+    d.batch, d.m_rows, d.n_tile_hint, d.grid_hint = B, m_rows, n_tile_hint, grid_hint or GRID_CAP
+    d.flush_adds = flush_adds or (FLUSH_ADDS if (f16 and W.hib) else 0)  # the "exact" formats always accumulate in chunks
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_conv_tc(ctypes.byref(d), ops._stream()), "ac_conv_tc")
     if ops._PROFILER:
@@ -275,7 +283,7 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
     d.fmt = (FMT_A_F16 if f16 else 0) | (FMT_W_HIB if W1.hib else 0) | (FMT_W2_HIB if W2.hib else 0) | \
             (FMT_Y_F16 if (y is not None and y.f16) else 0) | (FMT_YACT_F16 if (y_act is not None and y_act.f16) else 0) | \
             (FMT_RES_F16 if (res is not None and res.f16) else 0)
-    d.batch, d.m_rows, d.bk, d.g_hint, d.grid_hint, d.dbl_hint = B, m_rows, bk or pick_bk(cin), g_hint, grid_hint, dbl_hint
+    d.batch, d.m_rows, d.bk, d.g_hint, d.grid_hint, d.dbl_hint = B, m_rows, bk or pick_bk(cin), g_hint, grid_hint or GRID_CAP, dbl_hint
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_resunit_tc(ctypes.byref(d), ops._stream()), "ac_resunit_tc")
     if ops._PROFILER:

@@ -332,7 +332,15 @@ def parity_and_cpu_baseline(state, reps):
     ref64, est = ref64 - ref64.mean(1, keepdim=True), est - est.mean(1, keepdim=True)
     s = (est * ref64).sum(1, keepdim=True) / ref64.pow(2).sum(1, keepdim=True).clamp_min(1e-30) * ref64
     sisnr = (10 * torch.log10(s.pow(2).sum(1) / (est - s).pow(2).sum(1).clamp_min(1e-30))).min().item()
+    # residual quantisation is a chain: a frame is judged at its FIRST differing stage (later stages quantise another residual)
+    eqf, gf = eq.flatten(0, -2), gaps.flatten(0, -2)
+    diff = ~eqf
+    first = diff.float().argmax(-1)
+    gap_at = gf[torch.arange(eqf.shape[0]), first]
+    has = diff.any(-1)
     parity = {"code_match_safe": round(eq[safe].float().mean().item(), 6), "code_match_all": round(eq.float().mean().item(), 6),
+              "frames": int(eqf.shape[0]), "frames_first_diff_at_gap_gt_1e-4": int((has & (gap_at > 1e-4)).sum()),
+              "frames_first_diff_at_near_tie": int((has & (gap_at <= 1e-4)).sum()),
               "near_tie_frac": round((~safe).float().mean().item(), 6), "sisnr_db": round(sisnr, 2),
               "per_stage_match": [round(eq[..., k].float().mean().item(), 4) for k in range(eq.shape[-1])],
               "decisions": int(eq.numel()), "clips_checked": clips,

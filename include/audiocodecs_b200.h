@@ -112,6 +112,8 @@ typedef struct ac_lstm_tc_desc {
     int32_t out_fp16, skip_fp16; /* hi planes of out / final, and of skip, hold fp16 instead of bf16 (lo planes: bf16) */
 } ac_lstm_tc_desc;
 AC_API int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream);
+/* diagnostic: co-resident clusters of `cluster_size` CTAs of the recurrence kernel at `smem_bytes` of dynamic shared memory */
+AC_API int ac_lstm_tc_max_clusters(int32_t cluster_size, int32_t smem_bytes);
 
 /*
  * Residual VQ encode on tcgen05 tensor cores (dim 128 or 256, n_codes a multiple of 128 in [256, 2048]), all stages fused,
@@ -225,6 +227,9 @@ typedef struct ac_conv_tc_desc {
     const float* res32;          /* optional fp32 residual in the output's flat layout (clip stride res_bstride) */
     int32_t g_hint;              /* 128-row sub-tiles per tile (1, 2 or 4) sharing one A block and one W block; 0 = automatic */
     int32_t fmt;                 /* AC_FMT_* flags; 0 = everything bf16 */
+    int32_t flush_adds;          /* > 0: chunked accumulation -- at most about this many tcgen05.mma per partial sum, partials added
+                                    in fp32 round-to-nearest by the epilogue warps (the tensor-core accumulator truncates every add:
+                                    ~2e-8 of shrink per MMA, 2e-5 at K = 4096 with three products).  0 = one accumulator per tile */
 } ac_conv_tc_desc;
 
 AC_API int ac_conv_tc(const ac_conv_tc_desc* d, void* stream);

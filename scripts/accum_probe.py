@@ -12,7 +12,8 @@ FULL = tc.Policy(True, 0, True, True)
 ONE = tc.Policy(True, tc.NEVER, False)
 g = torch.Generator().manual_seed(1)
 M, N = 4096, 128
-for pol, pname in ((FULL, "3 products"), (ONE, "1 product")):
+for pol, pname, flush in ((FULL, "3 products", 0), (FULL, "3 products, chunked accumulation", 24), (ONE, "1 product", 0)):
+    tc.FLUSH_ADDS = flush
     for K in (64, 256, 1024, 4096):
         for mean in (0.0, 1.0):
             x = torch.randn(1, M, K, generator=g) + mean       # mean != 0: all-positive-ish partial sums (ELU-like common mode)

@@ -37,8 +37,11 @@ def rel(name, got, what="raw"):
     r = ref[name].transpose(1, 2)
     if what == "elu":
         r = F.elu(r)
-    e = ((got.double().cpu() - r).norm() / r.norm()).item()
-    print(f"{name:12s} {what:4s} rel err {e:.2e}", flush=True)
+    d = got.double().cpu() - r
+    e = (d.norm() / r.norm()).item()
+    alpha = ((d * r).sum() / (r * r).sum()).item()          # multiplicative bias: the part of the error that is a pure scaling
+    resid = ((d - alpha * r).norm() / r.norm()).item()
+    print(f"{name:12s} {what:4s} rel err {e:.2e}  (scaling part {alpha:+.2e}, rest {resid:.2e})", flush=True)
 
 
 pol = codec.pol_enc

@@ -26,3 +26,17 @@ def code_report(ours, ref, gaps):
     safe = gaps > NEAR_TIE_REL_GAP
     eq = ours.cpu() == ref
     return eq[safe].float().mean().item(), (~safe).float().mean().item(), eq.float().mean().item()
+
+
+def divergence_report(ours, ref, gaps):
+    """Residual quantisation is a chain: once a frame's stage-k code differs, its later stages quantise another residual and
+    their codes mean nothing.  So the north_star criterion ("bit-exact wherever the top-2 gap exceeds 1e-4, near-ties
+    reported separately") is read per FRAME at its FIRST differing stage: (frames whose first difference is a decision with
+    gap > 1e-4 -- violations, frames whose first difference is a near-tie -- excused, frames)."""
+    eq = (ours.cpu() == ref).flatten(0, -2)          # [frames, K]
+    g = gaps.flatten(0, -2)
+    diff = ~eq
+    first = torch.where(diff.any(-1), diff.float().argmax(-1), torch.full((eq.shape[0],), -1))
+    has = first >= 0
+    gap_at = g[torch.arange(eq.shape[0]), first.clamp(min=0)]
+    return int((has & (gap_at > NEAR_TIE_REL_GAP)).sum()), int((has & (gap_at <= NEAR_TIE_REL_GAP)).sum()), int(eq.shape[0])

@@ -8,7 +8,7 @@ the full BASELINE batch (64 / 64 / 128 clips) against the oracle, and bit-for-bi
 import pytest
 import torch
 
-from helpers import WAVE_SISNR_BF16_DB, code_report, make_input, si_snr_db
+from helpers import WAVE_SISNR_BF16_DB, code_report, divergence_report, make_input, si_snr_db
 from oracle import dac_ref, encodec_ref, mimi_ref
 
 pytestmark = pytest.mark.gpu
@@ -79,8 +79,10 @@ def _full_size(codec, ref_mod, sd, dev, B, T, K, pick, floors):
     per_stage = [round((got[..., k] == ref[..., k]).float().mean().item(), 4) for k in range(K)]
     rec = codec.toks_to_sig(ref.to(dev)).cpu()
     snr = si_snr_db(ref_rec, rec)
+    viol, excused, frames = divergence_report(got, ref, gaps)
     print(f"{type(codec).__name__} {codec.precision} {B}x{T}: code match safe {m_safe:.5f} all {m_all:.5f} near-ties {tie:.5f} "
-          f"per stage {per_stage} decoder SI-SNR {snr:.1f} dB")
+          f"per stage {per_stage} decoder SI-SNR {snr:.1f} dB; frames first differing at a safe decision {viol}, at a near-tie "
+          f"{excused}, of {frames}")
     assert m_safe >= floors[0] and m_all >= floors[1] and snr >= WAVE_SISNR_BF16_DB, (m_safe, m_all, snr)
     return toks
 
@@ -139,8 +141,10 @@ def test_encodec32_exact_all_stages(encodec_sd, dev):
     m_safe, tie, m_all = code_report(toks, ref, gaps)
     feats = codec.sig_to_feats(sig.to(dev)).cpu()
     rel = ((feats - emb.movedim(-1, -2)).norm() / emb.norm()).item()
-    print(f"EnCodec K=32 exact: embedding rel-err {rel:.2e}, code match safe {m_safe:.5f} all {m_all:.5f} near-ties {tie:.5f}")
-    assert rel < 6e-5 and m_safe >= 0.999, (rel, m_safe)
+    viol, excused, frames = divergence_report(toks, ref, gaps)
+    print(f"EnCodec K=32 exact: embedding rel-err {rel:.2e}, code match safe {m_safe:.5f} all {m_all:.5f} near-ties {tie:.5f}; "
+          f"frames first differing at a safe decision {viol}, at a near-tie {excused}, of {frames}")
+    assert rel < 2e-5 and m_safe >= 0.999 and viol <= 1, (rel, m_safe, viol)
 
 
 def test_device_guard_and_token_checks(encodec_sd, dev):

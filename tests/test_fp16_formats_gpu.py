@@ -108,6 +108,34 @@ def test_resunit_tc_formats(pol, tol, C, L, B, g, dbl):
     assert torch.isfinite(got).all() and err < tol, err
 
 
+@pytest.mark.parametrize("K,N", [(4096, 512), (3584, 128), (1280, 256)])
+def test_chunked_accumulation(K, N):
+    """The tcgen05 accumulator truncates every add (scripts/accum_probe.py): a K-deep contraction shrinks by ~2e-8 per MMA.
+    With chunked accumulation (partial sums of ~96 MMAs added in fp32 round-to-nearest by the epilogue warps) the error of
+    the "exact" formats no longer grows with K.  Shapes = EnCodec's deepest encoder contractions (down 256->512 k16,
+    512->128 k7, down 128->256 k10), positive-mean operands (the worst case: every partial sum has the same sign)."""
+    g = torch.Generator().manual_seed(K)
+    M = 700
+    x = torch.randn(2, M, K, generator=g) + 0.5
+    w = (torch.randn(N, K, generator=g) + 0.5) * K ** -0.5
+    a = FULL.act(2, M, K, DEV)
+    _fill(a, x)
+    W = _to_dev(FULL.weights(w, None))
+    ref = x.double() @ w.double().t()
+    errs = {}
+    for flush in (0, 96):
+        y32 = torch.empty((2, M, N), device=DEV, dtype=torch.float32)
+        saved, tc.FLUSH_ADDS = tc.FLUSH_ADDS, flush
+        try:
+            tc.conv_tc(W, [Src(a)], M, y32=y32)
+        finally:
+            tc.FLUSH_ADDS = saved
+        torch.cuda.synchronize()
+        errs[flush] = ((y32.cpu().double() - ref).norm() / ref.norm()).item()
+    print(f"K={K} N={N}: rel err one accumulator {errs[0]:.2e}, chunked {errs[96]:.2e}")
+    assert errs[96] < 2.5e-6 and errs[96] < errs[0] / 2
+
+
 def test_fp16_saturates_instead_of_inf():
     """values beyond the fp16 range come out as +-65504 in the hi plane (cvt.satfinite), never inf; the bf16 lo plane of a
     pair then carries the remainder (precision degrades gracefully to ~bf16)."""
