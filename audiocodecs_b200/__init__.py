@@ -8,6 +8,7 @@ from .encodec import Encodec
 from .mimi import Mimi
 from . import shard  # noqa: F401  (clip sharding across GPUs)
 from .graphs import GraphedCodec
+from .consumers import CodebookUtil, MultiHeadEmbedding
 
 __version__ = "0.1.0"
-__all__ = ["Codec", "Encodec", "DAC", "Mimi", "GraphedCodec"]
+__all__ = ["Codec", "Encodec", "DAC", "Mimi", "GraphedCodec", "CodebookUtil", "MultiHeadEmbedding"]

@@ -374,6 +374,21 @@ AC_API int ac_dac_rvq_decode_f32(const int64_t* codes, const float* codebooks, c
                                  float* out, int64_t rows, int32_t hidden, int32_t cb_dim, int32_t n_codes, int32_t stages,
                                  int32_t code_stride, int32_t* err_flag, void* stream);
 
+/*
+ * Token consumers (the step right after the tokenizer in the reference's downstream recipes):
+ * ac_token_histogram: counts[k][v] += #{rows r : toks[r][k] == v} -- the accumulation of CodebookUtil.append
+ *   (R/downstream/metrics/codebook_util.py:39-49); counts is int64 [num_codebooks][vocab_size], toks int64 [rows][num_codebooks];
+ *   out-of-range tokens set *err_flag and are not counted.
+ * ac_multihead_embedding: out[r][k][:] = weight[toks[r][k] + offsets[k]][:] (fp32, dim % 4 == 0) -- MultiHeadEmbedding.forward
+ *   (R/downstream/models/multihead.py:52-69); padding_row >= 0: a token equal to vocab_size reads that row (the shared padding
+ *   embedding), else -1.
+ */
+AC_API int ac_token_histogram(const int64_t* toks, int64_t rows, int32_t num_codebooks, int32_t vocab_size, int64_t* counts,
+                              int32_t* err_flag, void* stream);
+AC_API int ac_multihead_embedding(const int64_t* toks, const float* weight, const int64_t* offsets, float* out, int64_t rows,
+                                  int32_t num_codebooks, int32_t dim, int64_t vocab_size, int64_t padding_row,
+                                  int64_t num_embeddings, int32_t* err_flag, void* stream);
+
 AC_API int ac_abi_version(void);
 AC_API const char* ac_last_error(void);
 /* number of kernel launches issued through this library by the calling process (bench: gpu_launches) */
