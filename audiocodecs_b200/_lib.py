@@ -58,7 +58,7 @@ class AcResunitTcDesc(ctypes.Structure):
                 ("res", c_vp), ("res_lo", c_vp), ("res_bstride", c_i64),
                 ("y", c_vp), ("y_lo", c_vp), ("y_act", c_vp), ("y_act_lo", c_vp), ("y_bstride", c_i64), ("y_act_bstride", c_i64),
                 ("batch", c_i32), ("m_rows", c_i32), ("bk", c_i32), ("g_hint", c_i32), ("grid_hint", c_i32), ("dbl_hint", c_i32),
-                ("act0", c_i32), ("e_split", c_i32), ("x_from_a", c_i32), ("alpha0", c_vp), ("x_row_off", c_i32), ("fmt", c_i32)]
+                ("act0", c_i32), ("e_split", c_i32), ("x_from_a", c_i32), ("alpha0", c_vp), ("x_row_off", c_i32), ("fmt", c_i32), ("io_stage", c_i32)]
 
 
 class AcLstmTcDesc(ctypes.Structure):

@@ -18,6 +18,15 @@
 // GEMM2 of tile i; acc1 and the hidden tile are double-buffered whenever tensor memory allows (2*G*ch + G*cout <= 512
 // columns), so GEMM1 / epilogue 1 of tile i+1 run under GEMM2 / epilogue 2 of tile i and neither the tensor pipe (DAC) nor
 // the epilogue warps (EnCodec, Mimi) wait on the other between tiles.
+//
+// Staged epilogue I/O (io_stage): a lane owns an accumulator ROW, so a direct global load / store of its 32 bytes touches
+// 32 different 128-byte lines per warp instruction -- ncu showed the L1 data pipe at 55-84 % of its wavefront peak on DAC's
+// 64 / 128-channel units (profiles/r02_dac_fp16_resunit_raw.csv), the top stall long_scoreboard.  When shared memory allows,
+// the skip input tile is brought in by TMA (cp.async.bulk.tensor) into a swizzled staging buffer, epilogue 2 reads it there
+// and writes the raw / activated outputs into two more, and one thread sends the finished tiles out with TMA stores
+// (UTMASTG): coalesced 128-byte lines both ways, rows beyond m_rows clipped by the hardware.  The next tile's skip input is
+// requested as soon as every warp has read this one's, and the stores are only waited for when the next tile is about to
+// overwrite their buffers, so neither sits on the critical path.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -37,12 +46,13 @@ constexpr int FIRST_EPI_WARP = 3;
 constexpr int XF_WARPS = 4;  // transform warps: raw input block -> activated operand block (raw mode)
 constexpr int FIRST_XF_WARP = FIRST_EPI_WARP + EPI_WARPS;
 constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS + XF_WARPS);
-constexpr int NBARS = 4 * MAX_A_STAGES + 2 * MAX_W_STAGES + 8;
+constexpr int NBARS = 4 * MAX_A_STAGES + 2 * MAX_W_STAGES + 10;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_HALF = 113 * 1024;
 
 struct RuMaps {
     CUtensorMap a, a_lo, x, x_lo, w1, w2h, w2x;
+    CUtensorMap res, res_lo, y, y_lo, ya, ya_lo;   // staged epilogue I/O: [batch][rows][cout] views, box = (bko channels, 128 rows, 1)
 };
 
 struct RuParams {
@@ -60,6 +70,10 @@ struct RuParams {
     int raw, act0, e_split, x_from_a, sc_row_off;
     uint32_t e_stage_bytes, e_plane_bytes;
     const float* alpha0;
+    // staged epilogue I/O: planes [res hi][res lo][y hi][y lo][act hi][act lo] (those that exist) of io_plane_bytes each, a
+    // plane = cout/bko column blocks of G pieces of [128 rows][bko*2 bytes] in the TMA swizzle of that row width
+    int io_stage, bko, io_y_off, io_act_off, io_planes;   // plane index of the y / activated group
+    uint32_t io_plane_bytes, io_blk_bytes;
     int f16, w1_hib, w2_hib, y_f16, ya_f16, res_f16;  // formats (AC_FMT_*): hi planes fp16 / extra bf16(W) planes for the lo products
     int dbl;                      // acc1 and the hidden tile are double-buffered: GEMM1 / epilogue 1 of tile i+1 overlap GEMM2 / epilogue 2 of tile i
     uint32_t h_stage_bytes;       // one hidden-tile buffer (all k-blocks, hi [+lo] planes)
@@ -262,7 +276,8 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     uint8_t* e_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;  // activated blocks (raw mode only)
     uint8_t* w_area = e_ring + (p.raw ? (size_t)p.a_stages * p.e_stage_bytes : 0);
     uint8_t* h_tile = w_area + p.w_area_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(h_tile + (size_t)p.h_stage_bytes * (1 + p.dbl));
+    uint8_t* io_s = h_tile + (size_t)p.h_stage_bytes * (1 + p.dbl);   // staged epilogue I/O planes (1024-aligned: every part before is)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(io_s + (p.io_stage ? (size_t)p.io_plane_bytes * p.io_planes : 0));
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + MAX_A_STAGES;
     uint64_t* e_full = a_empty + MAX_A_STAGES;
@@ -274,7 +289,9 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     uint64_t* acc2_full = h_ready + 2;
     uint64_t* acc_free = acc2_full + 1;
     uint64_t* wres_bar = acc_free + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+    uint64_t* io_ready = wres_bar + 1;   // this tile's skip input has landed in the staging buffer
+    uint64_t* out_free = io_ready + 1;   // the previous tile's stores have read the output staging buffers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
     float* bias1_s = reinterpret_cast<float*>(bars + NBARS);  // 16-byte aligned: the barrier block is 1024-aligned, NBARS is even
     float* alpha1_s = bias1_s + p.ch;
     float* ralpha1_s = alpha1_s + p.ch;
@@ -305,6 +322,11 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         mbar_init(acc2_full, 1);
         mbar_init(acc_free, EPI_WARPS);
         mbar_init(wres_bar, 1);
+        mbar_init(io_ready, 1);
+        mbar_init(out_free, 1);
+        if (p.io_stage) {
+            prefetch_tensormap(&maps.res); prefetch_tensormap(&maps.y); prefetch_tensormap(&maps.ya);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -563,7 +585,128 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                 rnext[2] = l[0]; rnext[3] = l[1];
             }
         };
+        // ---------------- staged variant: skip input and outputs go through swizzled shared-memory tiles and TMA
+        const int io_units = p.bko / 8;                                   // 16-byte units per staged row
+        const int io_xshift = p.bko == 64 ? 0 : (p.bko == 32 ? 1 : 2);
+        const uint32_t io_row_bytes = p.bko * 2, io_piece_bytes = TILE_M * p.bko * 2;
+        const bool io_leader = warp == FIRST_EPI_WARP && lane == 0;
+        // TMA traffic of one tile: `load` brings the skip tile in (completing on io_ready), else sends the output planes out
+        auto io_tma = [&](int it, bool load) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int mg = tile % p.m_groups, b = tile / p.m_groups;
+            const int nblk = p.cout / p.bko;
+            for (int kb = 0; kb < nblk; ++kb)
+                for (int g = 0; g < p.G; ++g) {
+                    const int m0 = (mg * p.G + g) * TILE_M;
+                    if (m0 >= p.m_rows) continue;
+                    uint8_t* piece = io_s + (size_t)kb * p.io_blk_bytes + (size_t)g * io_piece_bytes;
+                    if (load) {
+                        tma_load_3d(piece, &maps.res, io_ready, kb * p.bko, m0, b);
+                        if (has_res_lo) tma_load_3d(piece + p.io_plane_bytes, &maps.res_lo, io_ready, kb * p.bko, m0, b);
+                    } else {
+                        if (p.y) {
+                            uint8_t* yp = piece + (size_t)p.io_y_off * p.io_plane_bytes;
+                            tma_store_3d(&maps.y, yp, kb * p.bko, m0, b);
+                            if (p.y_lo) tma_store_3d(&maps.y_lo, yp + p.io_plane_bytes, kb * p.bko, m0, b);
+                        }
+                        if (p.y_act) {
+                            uint8_t* ap = piece + (size_t)p.io_act_off * p.io_plane_bytes;
+                            tma_store_3d(&maps.ya, ap, kb * p.bko, m0, b);
+                            if (p.y_act_lo) tma_store_3d(&maps.ya_lo, ap + p.io_plane_bytes, kb * p.bko, m0, b);
+                        }
+                    }
+                }
+        };
+        // the skip-input buffer is free (every warp has read the previous tile's): request tile `it`'s
+        auto io_open = [&](int it) {
+            uint32_t bytes = 0;
+            if (has_res) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int mg = tile % p.m_groups;
+                int live = 0;
+                for (int g = 0; g < p.G; ++g) live += ((mg * p.G + g) * TILE_M < p.m_rows) ? 1 : 0;
+                bytes = (uint32_t)live * (uint32_t)(p.cout / p.bko) * io_piece_bytes * (1 + (has_res_lo ? 1 : 0));
+            }
+            if (bytes) { mbar_arrive_expect_tx(io_ready, bytes); io_tma(it, true); }
+            else mbar_arrive(io_ready);
+        };
+        if (p.io_stage && io_leader && my_tiles > 0) io_open(0);
+        auto epi2_staged = [&](int it) {
+            if (io_leader) {               // the previous tile's stores have had a whole tile's time to read their buffers
+                bulk_wait_read();
+                mbar_arrive(out_free);
+            }
+            mbar_wait(io_ready, it & 1);   // this tile's skip input has landed
+            mbar_wait(out_free, it & 1);
+            mbar_wait(acc2_full, it & 1);
+            tc_fence_after();
+            uint8_t* y_s = io_s + (size_t)p.io_y_off * p.io_plane_bytes;
+            uint8_t* act_s = io_s + (size_t)p.io_act_off * p.io_plane_bytes;
+            int g = 0, c = slot;
+            while (c >= c2) { c -= c2; ++g; }
+            for (int item = slot; item < p.G * c2; item += EPI_WARPS / 4) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + p.acc2_col + g * p.cout + c * 16, v);
+                const int row = quarter * 32 + lane;          // row inside the 128-row piece g
+                const int col = c * 16;
+                const int kb = col / p.bko, u0 = (col % p.bko) >> 3;
+                const int xr = (row >> io_xshift) & (io_units - 1);
+                const uint32_t off = (uint32_t)kb * p.io_blk_bytes + (uint32_t)g * io_piece_bytes + (uint32_t)row * io_row_bytes;
+                const uint32_t o0 = off + (((u0) ^ xr) << 4), o1 = off + (((u0 + 1) ^ xr) << 4);
+                c += EPI_WARPS / 4;
+                while (c >= c2) { c -= c2; ++g; }
+                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, l0 = r0, l1 = r0;
+                if (has_res) {
+                    r0 = *reinterpret_cast<const uint4*>(io_s + o0); r1 = *reinterpret_cast<const uint4*>(io_s + o1);
+                    if (has_res_lo) {
+                        l0 = *reinterpret_cast<const uint4*>(io_s + p.io_plane_bytes + o0);
+                        l1 = *reinterpret_cast<const uint4*>(io_s + p.io_plane_bytes + o1);
+                    }
+                }
+                tmem_ld_wait();
+                float o[16];
+                add_bias16(o, v, bias2_s + col);
+                if (has_res) {
+                    add_bf16x16(o, r0, r1, p.res_f16 != 0);
+                    if (has_res_lo) add_bf16x16(o, l0, l1);
+                }
+                if (p.y) {
+                    float oa[8], ob[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { oa[i] = o[i]; ob[i] = o[8 + i]; }
+                    const uint4 qa = pack8(oa, p.y_f16 != 0), qb = pack8(ob, p.y_f16 != 0);
+                    *reinterpret_cast<uint4*>(y_s + o0) = qa; *reinterpret_cast<uint4*>(y_s + o1) = qb;
+                    if (p.y_lo) {
+                        *reinterpret_cast<uint4*>(y_s + p.io_plane_bytes + o0) = pack_lo(oa, qa, p.y_f16 != 0);
+                        *reinterpret_cast<uint4*>(y_s + p.io_plane_bytes + o1) = pack_lo(ob, qb, p.y_f16 != 0);
+                    }
+                }
+                if (p.y_act) {
+                    apply_act(o, p.act2, alpha2_s, ralpha2_s, col);
+                    float oa[8], ob[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { oa[i] = o[i]; ob[i] = o[8 + i]; }
+                    const uint4 qa = pack8(oa, p.ya_f16 != 0), qb = pack8(ob, p.ya_f16 != 0);
+                    *reinterpret_cast<uint4*>(act_s + o0) = qa; *reinterpret_cast<uint4*>(act_s + o1) = qb;
+                    if (p.y_act_lo) {
+                        *reinterpret_cast<uint4*>(act_s + p.io_plane_bytes + o0) = pack_lo(oa, qa, p.ya_f16 != 0);
+                        *reinterpret_cast<uint4*>(act_s + p.io_plane_bytes + o1) = pack_lo(ob, qb, p.ya_f16 != 0);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);     // acc2 drained: GEMM2 of the next tile may start
+            fence_proxy_async();                      // generic-proxy writes of the staged tiles -> visible to the TMA stores
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // every epilogue warp has finished the tile
+            if (io_leader) {
+                io_tma(it, false);
+                bulk_commit();
+                if (it + 1 < my_tiles) io_open(it + 1);   // every warp has read this tile's skip input: fetch the next one's
+            }
+        };
         auto epi2 = [&](int it) {
+            if (p.io_stage) { epi2_staged(it); return; }
             const int tile = blockIdx.x + it * gridDim.x;
             const int mg = tile % p.m_groups;
             const int b = tile / p.m_groups;
@@ -610,6 +753,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
         } else {
             for (int it = 0; it < my_tiles; ++it) { epi1(it); epi2(it); }
         }
+        if (p.io_stage && io_leader) bulk_wait_all();   // the last tile's stores are complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -685,6 +829,11 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     // accumulated, i.e. the fp32 rounding of the result.  They must depend on the layer shape alone -- not on the batch size or
     // on the (G, double-buffering) variant a tuner asks for, or a clip's tokens would depend on its neighbours: the canonical
     // pair is the one the un-hinted G = 1 search settles on, and every other tiling is accepted only with that same pair.
+    // staged epilogue I/O: planes [raw hi][raw lo][act hi][act lo], each G*128 rows x cout (see the kernel header)
+    const int io_res = (d->res ? 1 : 0) + (d->res_lo ? 1 : 0), io_y = (d->y ? 1 : 0) + (d->y_lo ? 1 : 0), io_a = (d->y_act ? 1 : 0) + (d->y_act_lo ? 1 : 0);
+    const int io_planes = io_res + io_y + io_a;
+    const int bko = d->cout % 64 == 0 ? 64 : (d->cout % 32 == 0 ? 32 : 16);
+    bool use_io = d->io_stage >= 0 && !raw;
     auto search = [&](int g_only, int bk_only, int bkh_only, bool use_hint) -> bool {
     // pass 0: double-buffered hidden tile / acc1 with deep rings; pass 1: double-buffered, any rings; pass 2: single-buffered
     for (int pass = 0; pass < 3; ++pass)
@@ -724,8 +873,9 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 uint32_t cols = 32;
                 while (cols < (uint32_t)need_cols) cols <<= 1;
                 const size_t budget = SMEM_LIMIT - fixed;
-                if (h_total >= budget) continue;
-                const size_t rest = budget - h_total;
+                const size_t io_total = use_io ? (size_t)io_planes * G * TILE_M * d->cout * 2 : 0;
+                if (h_total + io_total >= budget) continue;
+                const size_t rest = budget - h_total - io_total;
                 int a_stages, w_stages = 0;
                 size_t w_area;
                 if (resident) {
@@ -765,11 +915,20 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
         }
     return false;
     };
+    // the canonical contraction blocks are those of the un-staged G = 1 search (staging must not change the arithmetic)
+    const bool want_io = use_io;
+    use_io = false;
     bool found = search(1, 0, 0, false);
     if (found) {
         const int bk_c = p.bk, bkh_c = p.bkh;
         const bool hinted = d->g_hint > 0 || d->dbl_hint >= 0;
-        if (!search(0, bk_c, bkh_c, true)) found = hinted ? false : search(1, bk_c, bkh_c, false);
+        use_io = want_io;
+        bool ok = use_io && search(0, bk_c, bkh_c, true);
+        if (!ok) {
+            AC_REQUIRE(d->io_stage <= 0, "ac_resunit_tc: staged epilogue I/O does not fit shared memory for this tiling");
+            use_io = false;
+            if (!search(0, bk_c, bkh_c, true)) found = hinted ? false : search(1, bk_c, bkh_c, false);
+        }
     }
     AC_REQUIRE(found, "ac_resunit_tc: no tiling fits shared memory (cin %d ch %d cout %d taps %d)", d->cin, d->ch, d->cout, d->taps);
 
@@ -800,6 +959,23 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     p.raw = raw; p.act0 = d->act0; p.e_split = e_split; p.x_from_a = x_from_a; p.sc_row_off = d->x_row_off; p.alpha0 = d->alpha0;
     p.cin = d->cin; p.taps = d->taps; p.dil = d->dilation; p.shift = d->shift; p.a_has_lo = a_has_lo; p.x_has_lo = x_has_lo;
     p.ch = d->ch; p.cout = d->cout; p.h_split = h_split; p.w1_split = w1_split; p.w2_split = w2_split;
+    p.io_stage = (found && use_io) ? 1 : 0; p.bko = bko; p.io_y_off = io_res; p.io_act_off = io_res + io_y; p.io_planes = io_planes;
+    p.io_blk_bytes = (uint32_t)p.G * TILE_M * bko * 2; p.io_plane_bytes = (uint32_t)p.G * TILE_M * d->cout * 2;
+    maps.res = maps.a; maps.res_lo = maps.a; maps.y = maps.a; maps.y_lo = maps.a; maps.ya = maps.a; maps.ya_lo = maps.a;
+    if (p.io_stage) {
+        auto io_map = [&](CUtensorMap* map, const void* base, int64_t bstride) -> int {
+            if (!base) return 0;
+            cuuint64_t gdim[3] = {(cuuint64_t)d->cout, (cuuint64_t)d->m_rows, (cuuint64_t)d->batch};
+            cuuint64_t gstr[2] = {(cuuint64_t)d->cout * 2, (cuuint64_t)bstride * 2};
+            cuuint32_t box[3] = {(cuuint32_t)bko, (cuuint32_t)TILE_M, 1};
+            cuuint32_t est[3] = {1, 1, 1};
+            return (int)encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle_for(bko), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        int e = io_map(&maps.res, d->res, d->res_bstride) | io_map(&maps.res_lo, d->res_lo, d->res_bstride) | io_map(&maps.y, d->y, d->y_bstride) |
+                io_map(&maps.y_lo, d->y_lo, d->y_bstride) | io_map(&maps.ya, d->y_act, d->y_act_bstride) | io_map(&maps.ya_lo, d->y_act_lo, d->y_act_bstride);
+        AC_REQUIRE(e == 0, "ac_resunit_tc: tensor map (staged epilogue I/O) failed: %d", e);
+    }
     p.f16 = f16; p.w1_hib = w1_hib; p.w2_hib = w2_hib;
     p.y_f16 = (d->fmt & AC_FMT_Y_F16) ? 1 : 0; p.ya_f16 = (d->fmt & AC_FMT_YACT_F16) ? 1 : 0; p.res_f16 = (d->fmt & AC_FMT_RES_F16) ? 1 : 0;
     p.m_rows = d->m_rows; p.m_groups = (d->m_rows + p.G * TILE_M - 1) / (p.G * TILE_M); p.batch = d->batch;
@@ -809,7 +985,8 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     p.res_bs = d->res_bstride; p.y_bs = d->y_bstride; p.ya_bs = d->y_act_bstride;
 
     // every CTA owns its SM (tensor memory is allocated in full): ask for more than half the shared memory
-    size_t smem = fixed + (size_t)p.a_stages * (p.a_stage_bytes + p.e_stage_bytes) + p.w_area_bytes + (size_t)p.h_stage_bytes * (1 + p.dbl);
+    size_t smem = fixed + (size_t)p.a_stages * (p.a_stage_bytes + p.e_stage_bytes) + p.w_area_bytes + (size_t)p.h_stage_bytes * (1 + p.dbl) +
+                  (p.io_stage ? (size_t)io_planes * p.io_plane_bytes : 0);
     AC_REQUIRE(smem <= (size_t)SMEM_LIMIT, "ac_resunit_tc: shared memory %zu", smem);
     if (smem <= (size_t)SMEM_HALF + 1024) smem = SMEM_HALF + 2048;
     static bool attr_set = false;

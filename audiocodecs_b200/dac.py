@@ -283,9 +283,9 @@ class DAC(Codec):
                 tc.conv_tc(W7, [a], L, y_act=hs, act=ACT_SNAKE, alpha=a2.t, name="res_k7_tc")
                 tc.conv_tc(W1, [Src(hs)], L, res=x, y=y, y_act=ys, act=ACT_SNAKE, alpha=nxt.t, name="res_k1_tc")
 
-            def fused(g, dbl, a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
+            def fused(g, dbl, io, a=a, x=x, y=y, ys=ys, W7=W7, W1=W1, a2=a2, nxt=nxt):
                 return lambda: tc.resunit_tc(W7, W1, a, L, res=x, y=y, y_act=ys, act1=ACT_SNAKE, alpha1=a2.t, act2=ACT_SNAKE,
-                                             alpha2=nxt.t, h_split=pol.split(C), g_hint=g, dbl_hint=dbl, name="resunit_tc")
+                                             alpha2=nxt.t, h_split=pol.split(C), g_hint=g, dbl_hint=dbl, io_stage=io, name="resunit_tc")
 
             # one fused launch (hidden tensor on chip) when both accumulators fit tensor memory, or two tap-GEMM launches.
             # Encoder: fused whenever it fits -- a rule, because the two forms group the fp32 accumulation differently and a
@@ -293,7 +293,8 @@ class DAC(Codec):
             # buffering).  Decoder: the measured-fastest form per layer shape (waveforms agree to ~1e-5 either way)
             variants = [("unfused", unfused)]
             if 2 * C <= 512:
-                fv = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (2, 1) for dbl in (1, 0)]
+                # io: 1 = skip input / outputs staged in shared memory and moved by TMA, -1 = direct loads / stores (bit-identical)
+                fv = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (2, 1) for dbl in (1, 0) for io in (-1, 1)]
                 variants = fv if enc else fv + variants
             tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc, xs.f16, W7.planes, W1.planes), variants)
             x, xs = y, ys

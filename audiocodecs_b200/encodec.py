@@ -269,11 +269,12 @@ class Encodec(Codec):
             tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
             tc.conv_tc(Wtail, [Src(he), Src(x)], L, y_act=ye, act=ACT_ELU, name="res_tail_tc")
 
-        def fused(g, dbl):
+        def fused(g, dbl, io):
             return lambda: tc.resunit_tc(Wk3, Wtail, a, L, x=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
-                                         name="resblock_tc")
+                                         io_stage=io, name="resblock_tc")
 
-        variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
+        # io: 1 = outputs staged in shared memory and sent out by TMA stores, -1 = direct stores (bit-identical results)
+        variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (1, 0) for io in (-1, 1)]
         if FUSED_MAX_CH is None:
             variants.append(("unfused", unfused))
         elif C > FUSED_MAX_CH:

@@ -224,16 +224,16 @@ class Mimi(Codec):
             tc.conv_tc(Wk3, [a], L, y_act=he, act=ACT_ELU, name="res_k3_tc")
             tc.conv_tc(Wk1, [Src(he)], L, res=x, y_act=ye, act=ACT_ELU, name="res_k1_tc")
 
-        def fused(g, dbl):
+        def fused(g, dbl, io):
             return lambda: tc.resunit_tc(Wk3, Wk1, a, L, res=x, y_act=ye, act1=ACT_ELU, act2=ACT_ELU, h_split=hs, g_hint=g, dbl_hint=dbl,
-                                         name="resblock_tc")
+                                         io_stage=io, name="resblock_tc")
 
         # fused (hidden activation on chip) whenever the accumulators fit tensor memory (measured faster at 64-256 channels),
         # else two launches.  A rule, not a timing: the two forms group the fp32 accumulation differently, and a clip's tokens
         # must not depend on the batch it is tuned in; the tuner only picks the tile grouping / buffering (bit-identical)
         variants = [("unfused", unfused)]
         if C <= 256:
-            variants = [(f"fused_g{g}_d{dbl}", fused(g, dbl)) for g in (4, 2, 1) for dbl in (1, 0)]
+            variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (1, 0) for io in (-1, 1)]
         tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs, x.f16, Wk3.planes, Wk1.planes), variants)
 
     def _tc_transformer(self, layers, tws, h, pol):

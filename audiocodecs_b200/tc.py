@@ -15,6 +15,9 @@ from . import _lib, ops
 from ._lib import AcConvTcDesc, AcResunitTcDesc
 
 
+IO_STAGE = int(__import__("os").environ.get("AC_IO_STAGE", "-1"))  # fused units launched without an explicit io_stage: -1 = direct
+                                                                    # global loads / stores, 0 = staged (TMA) when it fits.  The codecs
+                                                                    # let the tuner time both forms per layer (bit-identical results)
 FLUSH_ADDS = 96  # "exact" launches: tcgen05.mma per partial sum of the chunked accumulation (see csrc/conv_tc.cu); 0 = off.
                  # Measured on the EnCodec encoder (scripts/encoder_error_probe.py): embedding error 3.1e-5 with one accumulator
                  # per tile, 6.9e-6 at 24 (+1.2 ms per step: grouped tiles no longer fit tensor memory), about the same at 96
@@ -243,7 +246,7 @@ def conv_tc(W: TcWeights, srcs, m_rows, *, y: Act = None, y_act: Act = None, y32
 
 def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, res: Act = None, y: Act = None, y_act: Act = None,
                act1=ops.ACT_ELU, alpha1=None, act2=ops.ACT_NONE, alpha2=None, h_split=False, bk=None, g_hint=0, grid_hint=0,
-               dbl_hint=-1, act0=ops.ACT_NONE, alpha0=None, e_split=False, x_from_a=False, name="resunit_tc"):
+               dbl_hint=-1, act0=ops.ACT_NONE, alpha0=None, e_split=False, x_from_a=False, io_stage=0, name="resunit_tc"):
     """Fused residual unit (`ac_resunit_tc`): h = act1(conv_taps(a)); v = W2 [h | x] (+ res); y = v, y_act = act2(v).
     `a` is a Src view of the ACTIVATED input (taps / dilation / shift / origin as for conv_tc); x: raw input of a conv
     shortcut; res: identity skip.  With act0 the view is of the RAW input and the kernel applies the unit's input activation on
@@ -284,6 +287,7 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
             (FMT_Y_F16 if (y is not None and y.f16) else 0) | (FMT_YACT_F16 if (y_act is not None and y_act.f16) else 0) | \
             (FMT_RES_F16 if (res is not None and res.f16) else 0)
     d.batch, d.m_rows, d.bk, d.g_hint, d.grid_hint, d.dbl_hint = B, m_rows, bk or pick_bk(cin), g_hint, grid_hint or GRID_CAP, dbl_hint
+    d.io_stage = io_stage or IO_STAGE
     t0 = ops._PROFILER.begin() if ops._PROFILER else None
     _lib.check(_lib.lib().ac_resunit_tc(ctypes.byref(d), ops._stream()), "ac_resunit_tc")
     if ops._PROFILER:

@@ -274,6 +274,8 @@ typedef struct ac_resunit_tc_desc {
     const float* alpha0;
     int32_t x_row_off;                     /* x_from_a: view row (m + shift + x_row_off) holds raw x[m]; 0 <= x_row_off <= (taps-1)*dilation */
     int32_t fmt;                           /* AC_FMT_* flags; 0 = everything bf16 (raw mode, act0 != NONE, is bf16 only) */
+    int32_t io_stage;                      /* epilogue-2 I/O through shared-memory tiles + TMA loads / stores: 0 = when it fits shared
+                                              memory, -1 = never (direct global loads / stores), 1 = required (else an error) */
 } ac_resunit_tc_desc;
 
 AC_API int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream);

@@ -136,6 +136,42 @@ def test_chunked_accumulation(K, N):
     assert errs[96] < 2.5e-6 and errs[96] < errs[0] / 2
 
 
+@pytest.mark.parametrize("pol", [ONE, FULL, BF])
+@pytest.mark.parametrize("C,L,B,dil,g", [(64, 900, 2, 1, 2), (96, 500, 2, 9, 1), (128, 641, 1, 3, 1), (192, 300, 2, 9, 1)])
+def test_staged_epilogue_io_is_bit_identical(pol, C, L, B, dil, g):
+    """DAC residual unit y = x + conv1(Snake(conv7_dilated(Snake(x)))) with the skip input and both outputs (raw + activated)
+    moved by TMA through shared-memory tiles (io_stage=1: cp.async.bulk.tensor loads / stores, rows beyond L clipped by the
+    hardware) against the direct per-lane global loads / stores: the same bits, ragged lengths included."""
+    from audiocodecs_b200 import _lib
+    gen = torch.Generator().manual_seed(500 + C + dil)
+    x = torch.randn(B, L, C, generator=gen)
+    al1, al2, al3 = (torch.rand(C, generator=gen) + 0.5 for _ in range(3))
+    w7 = torch.randn(C, C, 7, generator=gen) * (7 * C) ** -0.5
+    w1 = torch.randn(C, C, generator=gen) * C ** -0.5
+    xa, xs = pol.act(B, L, C, DEV, split=pol.f16 is False or pol.full), pol.act(B, L, C, DEV)
+    _fill(xa, x)
+    _fill(xs, x + torch.sin(al1 * x) ** 2 / (al1 + 1e-9))
+    W7 = _to_dev(pol.weights(w7.permute(0, 2, 1).reshape(C, -1), torch.zeros(C)))
+    W1 = _to_dev(pol.weights(w1, torch.zeros(C)))
+    outs = {}
+    for io in (-1, 1):
+        y, ys = pol.act(B, L, C, DEV, split=xa.lo is not None, hl=3, hr=5), pol.act(B, L, C, DEV)
+        for t in (y.buf, ys.buf) + ((y.lo,) if y.lo is not None else ()) + ((ys.lo,) if ys.lo is not None else ()):
+            t.fill_(7.0)   # sentinel: halo rows and the neighbouring clip must stay untouched
+        try:
+            tc.resunit_tc(W7, W1, Src(xs, taps=7, dilation=dil, shift=-3 * dil), L, res=xa, y=y, y_act=ys, act1=ops.ACT_SNAKE, alpha1=al2.to(DEV),
+                          act2=ops.ACT_SNAKE, alpha2=al3.to(DEV), h_split=pol.split(C), g_hint=g, io_stage=io)
+        except _lib.ConfigError:
+            pytest.skip("staging does not fit shared memory for this tiling")
+        torch.cuda.synchronize()
+        outs[io] = [t.clone() for t in (y.buf, ys.buf) + ((y.lo,) if y.lo is not None else ()) + ((ys.lo,) if ys.lo is not None else ())]
+    for a, b in zip(outs[-1], outs[1]):
+        assert torch.equal(a, b)
+    assert (outs[1][0][:, :3] == 7.0).all() and (outs[1][0][:, 3 + L:] == 7.0).all()   # halos of y untouched
+    ref = x.double()
+    assert torch.isfinite(outs[1][1].float()).all()
+
+
 def test_fp16_saturates_instead_of_inf():
     """values beyond the fp16 range come out as +-65504 in the hi plane (cvt.satfinite), never inf; the bf16 lo plane of a
     pair then carries the remainder (precision degrades gracefully to ~bf16)."""
