@@ -40,13 +40,17 @@ WORKLOADS = {
 
 
 # per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, averaged over every launch of the kernel in one
-# full-size step at the default precision) from the committed ncu launch lists profiles/r02_*launches.csv; None = not captured
+# full-size tuned step) from the committed ncu launch lists profiles/r02_<codec>_<precision>_launches.csv; None = not captured
 NCU_TRAFFIC = {
-    "encodec": {"conv_tc_kernel": 1.194e9, "resunit_tc_kernel": 2.909e9, "lstm_tc_kernel": 4.77e8, "rvq_encode_tc_kernel": 3.3e7},
-    "mimi": {"conv_tc_kernel": 8.84e8, "resunit_tc_kernel": 9.416e9, "attention_tc_kernel": 2.38e8},
-    "dac": {"conv_tc_kernel": 8.431e9, "resunit_tc_kernel": 2.2226e10},
+    ("encodec", "exact"): {"conv_tc_kernel": 1.282e9, "resunit_tc_kernel": 4.387e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
+    ("encodec", "fp16"): {"conv_tc_kernel": 8.91e8, "resunit_tc_kernel": 2.911e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
+    ("mimi", "exact"): {"conv_tc_kernel": 7.70e8, "resunit_tc_kernel": 1.0017e10, "attention_tc_kernel": 2.27e8},
+    ("mimi", "fp16"): {"conv_tc_kernel": 5.51e8, "resunit_tc_kernel": 6.660e9, "attention_tc_kernel": 2.16e8},
+    ("dac", "exact"): {"conv_tc_kernel": 6.047e9, "resunit_tc_kernel": 2.1263e10},
+    ("dac", "fp16"): {"conv_tc_kernel": 5.098e9, "resunit_tc_kernel": 1.4093e10},
 }
-NCU_TRAFFIC["encodec32"] = NCU_TRAFFIC["encodec"]
+for _p in ("exact", "fp16"):
+    NCU_TRAFFIC[("encodec32", _p)] = NCU_TRAFFIC[("encodec", _p)]
 
 
 def load_peaks():
@@ -269,7 +273,7 @@ def measure(ctx, name, precision, steps, warmup, batch=0, sample_clocks=False, w
         roofline = {"kernel": kname, "bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                     "frac": round(tflops / peaks["tf_sus"], 4)}
     total_ms = sum(v["ms"] for v in summary.values())
-    roofline.update({"traffic": NCU_TRAFFIC.get(name, {}).get(kname),
+    roofline.update({"traffic": NCU_TRAFFIC.get((name, precision), {}).get(kname),
                      "peak_source": peaks["src"] + (" (copy bandwidth)" if roofline["bound"] == "hbm" else " (sustained bf16)"),
                      "flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
                      "tensor_tflops": round(tflops, 2), "launches_per_step": d["n"], "ms_per_step": round(d["ms"], 3),
