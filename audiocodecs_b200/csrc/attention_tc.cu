@@ -97,7 +97,7 @@ __device__ __forceinline__ void stage_plain(const float* base, size_t row_stride
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* q_hi = smem;
     uint8_t* q_lo = q_hi + Q_PLANE;
     uint8_t* k_hi = q_lo + Q_PLANE;

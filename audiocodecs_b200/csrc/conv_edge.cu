@@ -27,6 +27,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ELU through one bare MUFU.EX2 (same form as tcc::elu_ex2 of the tensor-path epilogues)
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.0f;
+}
+
 // Snake with the hardware sine, as in the tensor-path epilogues (the output is rounded to bf16)
 __device__ __forceinline__ float snake_fast(float x, float a, float ra) {
     const float s = __sinf(a * x);
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(C * 4) conv_first_kernel(const FirstP p) {
             float a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                a[c] = ACT == AC_ACT_ELU ? (acc[c] > 0.f ? acc[c] : exp2f(acc[c] * 1.4426950408889634f) - 1.0f)
+                a[c] = ACT == AC_ACT_ELU ? elu_fast(acc[c])
                                          : (ACT == AC_ACT_SNAKE ? snake_fast(acc[c], al[c], ral[c]) : acc[c]);
             store8_split(a, p.y_act + (long long)b * p.ya_bs + off, p.y_act_lo ? p.y_act_lo + (long long)b * p.ya_bs + off : nullptr, p.out_f16 != 0);
         }

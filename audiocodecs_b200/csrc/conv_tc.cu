@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-B aligned: round up to 1024 for the swizzled tiles
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* a_ring = smem;
     uint8_t* w_area = smem + (size_t)p.a_stages * p.a_stage_bytes;
     const size_t w_area_bytes = p.w_resident ? (size_t)p.w_res_plane * (1 + p.w_split + p.w_hib) : (size_t)p.w_stages * p.w_stage_bytes;

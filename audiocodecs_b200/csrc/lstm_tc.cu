@@ -125,7 +125,7 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* b_s = smem;                         // h operand: 2 parities x 16 KB, un-swizzled K-major core matrices
     uint8_t* hs = b_s + 2 * B_BYTES;             // 2 x 1 KB: this CTA's new h slice, already in operand layout
     float* gs = reinterpret_cast<float*>(hs + 2 * SLICE_BYTES);       // [4][32][17] activated gates

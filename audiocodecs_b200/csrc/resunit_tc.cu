@@ -271,7 +271,7 @@ template <bool RAW>
 __global__ void __launch_bounds__(RAW ? THREADS : THREADS - 32 * XF_WARPS, 1)
 resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ RuParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* a_ring = smem;
     uint8_t* e_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;  // activated blocks (raw mode only)
     uint8_t* w_area = e_ring + (p.raw ? (size_t)p.a_stages * p.e_stage_bytes : 0);

@@ -89,7 +89,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
     constexpr int HD = D / 2;                        // dims owned by one thread of a frame
     constexpr uint32_t A_PLANE_BYTES = KB * PLANE_KB_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + A_PLANE_BYTES;
     uint8_t* ring = a_lo + A_PLANE_BYTES;

@@ -9,6 +9,13 @@ namespace sm100 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Dynamic shared memory rounded up to 1024 bytes (swizzled TMA / UMMA tiles).  Pointer arithmetic on the __shared__ array
+// itself -- not a round trip through uintptr_t -- so the compiler keeps the shared address space and emits LDS / STS
+// instead of generic LD / ST for everything derived from it.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+    return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

@@ -104,9 +104,19 @@ __device__ __forceinline__ uint4 pack8(const float (&o)[8], bool f16 = false) {
     return make_uint4(pack16(o[0], o[1], f16), pack16(o[2], o[3], f16), pack16(o[4], o[5], f16), pack16(o[6], o[7], f16));
 }
 
-// ELU on the epilogue: exp through MUFU.EX2; abs error ~1e-7 (cancellation in exp(x)-1 near 0), far below the bf16 /
-// split-bf16 rounding that follows.
-__device__ __forceinline__ float elu_ex2(float x) { return x > 0.f ? x : exp2f(x * 1.4426950408889634f) - 1.0f; }
+// ELU on the epilogue: exp through one bare MUFU.EX2 (ex2.approx.ftz: no range fix-up code -- results below 2^-126 flush
+// to zero, i.e. ELU = -1 exactly as fp32 rounds it; exp2f() spent ~5 extra instructions per element on that range handling,
+// profiles/r02 source page); branch-free, abs error ~1e-7 (cancellation in exp(x)-1 near 0), far below the 16-bit rounding
+// that follows.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float elu_ex2(float x) {
+    const float e = ex2_approx(x * 1.4426950408889634f) - 1.0f;
+    return x > 0.f ? x : e;
+}
 
 
 // ------------------------------------------------------------------------------------------------ host
