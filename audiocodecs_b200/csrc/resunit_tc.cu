@@ -30,6 +30,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#define AC_MBAR_SUSPEND_NS 20000u   // throughput kernel: sleeping waits (see sm100.cuh)
 #include "sm100.cuh"
 #include "tc_common.cuh"
 

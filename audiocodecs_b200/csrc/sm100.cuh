@@ -39,8 +39,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint of a failed try_wait (ns): the waiting thread may sleep in hardware up to this long before the instruction
+// returns false.  Without a hint a waiting warp re-issues its ~9-instruction poll loop every ~160 ns -- 20-30 % of all executed
+// instructions of the fused-unit kernels were such polls (ncu source page).  Measured: step times of the throughput kernels
+// (conv_tc, resunit_tc) unchanged within the +-2 % run-to-run spread, fewer issued instructions; the latency-bound LSTM / RVQ
+// kernels lose 3-4 % (a hinted wait wakes a little later).  So a translation unit opts in by defining AC_MBAR_SUSPEND_NS
+// before this header.
+#ifndef AC_MBAR_SUSPEND_NS
+#define AC_MBAR_SUSPEND_NS 0u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if AC_MBAR_SUSPEND_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(AC_MBAR_SUSPEND_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -48,6 +66,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (surfacing as a launch error) instead of hanging the GPU.

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 T=${TAG:-r2r}
-timeout 900 python -m pytest tests/test_resunit_tc_gpu.py tests/test_dac_bf16_gpu.py tests/test_exact_gpu.py tests/test_fp16_formats_gpu.py -m gpu -q -x 2>&1 | tail -3
-for spec in "dac fp16 64" "encodec fp16 64" "mimi fp16 128" "dac exact 64"; do
+timeout 900 python -m pytest tests/test_resunit_tc_gpu.py tests/test_conv_tc_gpu.py tests/test_encodec_bf16_gpu.py -m gpu -q -x 2>&1 | tail -3
+for spec in "dac fp16 64" "encodec fp16 64" "encodec exact 64" "mimi fp16 128"; do
   set -- $spec
   AC_PRECISION=$2 timeout 400 python scripts/layer_times.py $1 $3 10 > gpurun_out/${T}_layers_$1_$2.txt 2>&1
   echo "$(grep '^total' gpurun_out/${T}_layers_$1_$2.txt || tail -2 gpurun_out/${T}_layers_$1_$2.txt)"
