@@ -119,6 +119,7 @@ def lib():
         L.ac_multihead_embedding.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp]
         L.ac_lstm_tc_max_clusters.argtypes = [c_i32, c_i32]
         L.ac_pad_halo_bf16.argtypes = [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
+        L.ac_pad_halo2_bf16.argtypes = [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]
         _lib = L
     return _lib
 

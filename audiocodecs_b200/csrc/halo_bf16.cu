@@ -8,10 +8,10 @@
 #include "tc_common.cuh"
 
 namespace {
-__global__ void pad_halo_bf16_kernel(__nv_bfloat16* data, int rows, int ch, long long bstride, int halo_l, int halo_r,
-                                     int mode, int reflect_len) {
+__global__ void pad_halo_bf16_kernel(__nv_bfloat16* data, __nv_bfloat16* data_lo, int rows, int ch, long long bstride, int halo_l,
+                                     int halo_r, int mode, int reflect_len) {
     const int b = blockIdx.y;
-    __nv_bfloat16* base = data + (long long)b * bstride;
+    __nv_bfloat16* base = (blockIdx.z ? data_lo : data) + (long long)b * bstride;   // z = 1: the lo plane of the same tensor
     const int total = (halo_l + halo_r) * ch;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int hr = e / ch, c = e % ch;
@@ -99,13 +99,18 @@ extern "C" int ac_add_act_bf16(const void* a_hi, const void* a_lo, const void* b
     return ac::finish_launch("ac_add_act_bf16");
 }
 
-extern "C" int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
-                                int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream) {
+extern "C" int ac_pad_halo2_bf16(void* data, void* data_lo, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
+                                 int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream) {
     AC_REQUIRE(data && batch > 0 && batch <= 65535 && rows > 0 && ch > 0, "ac_pad_halo_bf16: bad arguments");
     if (halo_l + halo_r <= 0) return 0;
     const int total = (halo_l + halo_r) * ch;
-    dim3 grid((total + 255) / 256 > 64 ? 64 : (total + 255) / 256, batch);
-    pad_halo_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)data, rows, ch, batch_stride, halo_l, halo_r,
-                                                                  mode, reflect_len < rows ? rows : reflect_len);
+    dim3 grid((total + 255) / 256 > 64 ? 64 : (total + 255) / 256, batch, data_lo ? 2 : 1);
+    pad_halo_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)data, (__nv_bfloat16*)data_lo, rows, ch, batch_stride,
+                                                                  halo_l, halo_r, mode, reflect_len < rows ? rows : reflect_len);
     return ac::finish_launch("ac_pad_halo_bf16");
+}
+
+extern "C" int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
+                                int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream) {
+    return ac_pad_halo2_bf16(data, nullptr, batch, rows, ch, batch_stride, halo_l, halo_r, mode, reflect_len, stream);
 }

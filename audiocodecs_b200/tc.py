@@ -78,10 +78,9 @@ class Act:
         if self.hl + self.hr == 0:
             return
         t0 = ops._PROFILER.begin() if ops._PROFILER else None
-        for ptr in (self.row_ptr(0), self.lo_ptr(0)):
-            if ptr is not None:
-                _lib.check(_lib.lib().ac_pad_halo_bf16(ctypes.c_void_p(ptr), self.B, self.L, self.C, self.bstride, self.hl,
-                                                       self.hr, mode, max(reflect_len, self.L), ops._stream()), "ac_pad_halo_bf16")
+        _lib.check(_lib.lib().ac_pad_halo2_bf16(ctypes.c_void_p(self.row_ptr(0)), ctypes.c_void_p(self.lo_ptr(0)), self.B, self.L, self.C,
+                                                self.bstride, self.hl, self.hr, mode, max(reflect_len, self.L), ops._stream()),
+                   "ac_pad_halo_bf16")   # both planes in one launch
         if ops._PROFILER:
             ops._PROFILER.end("pad_halo_bf16", t0, 0.0, 4.0 * self.B * (self.hl + self.hr) * self.C)
 

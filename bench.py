@@ -42,12 +42,12 @@ WORKLOADS = {
 # per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, averaged over every launch of the kernel in one
 # full-size tuned step) from the committed ncu launch lists profiles/r02_<codec>_<precision>_launches.csv; None = not captured
 NCU_TRAFFIC = {
-    ("encodec", "exact"): {"conv_tc_kernel": 1.282e9, "resunit_tc_kernel": 4.387e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
-    ("encodec", "fp16"): {"conv_tc_kernel": 8.91e8, "resunit_tc_kernel": 2.911e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
-    ("mimi", "exact"): {"conv_tc_kernel": 7.70e8, "resunit_tc_kernel": 1.0017e10, "attention_tc_kernel": 2.27e8},
-    ("mimi", "fp16"): {"conv_tc_kernel": 5.51e8, "resunit_tc_kernel": 6.660e9, "attention_tc_kernel": 2.16e8},
-    ("dac", "exact"): {"conv_tc_kernel": 6.047e9, "resunit_tc_kernel": 2.1263e10},
-    ("dac", "fp16"): {"conv_tc_kernel": 5.098e9, "resunit_tc_kernel": 1.4093e10},
+    ("encodec", "exact"): {"conv_tc_kernel": 1.282e9, "resunit_tc_kernel": 4.389e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
+    ("encodec", "fp16"): {"conv_tc_kernel": 8.92e8, "resunit_tc_kernel": 2.910e9, "lstm_tc_kernel": 4.76e8, "rvq_encode_tc_kernel": 3.3e7},
+    ("mimi", "exact"): {"conv_tc_kernel": 7.71e8, "resunit_tc_kernel": 1.0007e10, "attention_tc_kernel": 2.27e8},
+    ("mimi", "fp16"): {"conv_tc_kernel": 5.51e8, "resunit_tc_kernel": 6.650e9, "attention_tc_kernel": 2.16e8},
+    ("dac", "exact"): {"conv_tc_kernel": 6.023e9, "resunit_tc_kernel": 2.1198e10},
+    ("dac", "fp16"): {"conv_tc_kernel": 4.332e9, "resunit_tc_kernel": 1.4572e10},
 }
 for _p in ("exact", "fp16"):
     NCU_TRAFFIC[("encodec32", _p)] = NCU_TRAFFIC[("encodec", _p)]
@@ -100,7 +100,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:

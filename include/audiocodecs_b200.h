@@ -287,6 +287,9 @@ AC_API int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream);
  */
 AC_API int ac_pad_halo_bf16(void* data, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
                             int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream);
+/* the same for the (hi, lo) planes of one tensor in ONE launch (data_lo may be NULL): same geometry for both planes */
+AC_API int ac_pad_halo2_bf16(void* data, void* data_lo, int32_t batch, int32_t rows, int32_t ch, int64_t batch_stride,
+                             int32_t halo_l, int32_t halo_r, int32_t mode, int32_t reflect_len, void* stream);
 
 /*
  * out = act(a + b) elementwise on split-bf16 activations (hi plane + optional lo plane each), `per_clip` elements per
