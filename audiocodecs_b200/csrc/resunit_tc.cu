@@ -47,7 +47,7 @@ constexpr int FIRST_EPI_WARP = 3;
 constexpr int XF_WARPS = 4;  // transform warps: raw input block -> activated operand block (raw mode)
 constexpr int FIRST_XF_WARP = FIRST_EPI_WARP + EPI_WARPS;
 constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS + XF_WARPS);
-constexpr int NBARS = 4 * MAX_A_STAGES + 2 * MAX_W_STAGES + 10;
+constexpr int NBARS = 4 * MAX_A_STAGES + 2 * MAX_W_STAGES + 12;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_HALF = 113 * 1024;
 
@@ -77,6 +77,10 @@ struct RuParams {
     uint32_t io_plane_bytes, io_blk_bytes;
     int f16, w1_hib, w2_hib, y_f16, ya_f16, res_f16;  // formats (AC_FMT_*): hi planes fp16 / extra bf16(W) planes for the lo products
     int dbl;                      // acc1 and the hidden tile are double-buffered: GEMM1 / epilogue 1 of tile i+1 overlap GEMM2 / epilogue 2 of tile i
+    int pp;                       // ping-pong (needs dbl): acc2 is double-buffered too and the epilogue warps form two groups of eight that
+                                  // take alternate tiles, each running epilogue 1 and epilogue 2 of ITS tile -- two tiles in different
+                                  // phases (TMEM loads + activation + shared stores vs skip loads + global stores) share the SM's pipes
+    uint32_t acc2_stride;         // columns between the two acc2 buffers
     uint32_t h_stage_bytes;       // one hidden-tile buffer (all k-blocks, hi [+lo] planes)
     const float *bias1, *alpha1, *bias2, *alpha2;
     int act1, act2;
@@ -132,7 +136,6 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
     const uint32_t hib1 = p.w1_hib ? (uint32_t)(1 + p.w1_split) : 0u, hib2 = p.w2_hib ? (uint32_t)(1 + p.w2_split) : 0u;
     constexpr uint32_t row_bytes = KA * 32;
     const uint32_t a_ring_u = smem_u32(a_ring), e_ring_u = smem_u32(e_ring), w_area_u = smem_u32(w_area), h_u = smem_u32(h_tile);
-    const uint32_t acc2 = tmem_base + p.acc2_col;
     int a_base[2] = {0, 0};  // ring stage of chunk 0 of the tiles in flight (raw rows are read again by GEMM2's shortcut)
     if (p.w_resident) { mbar_wait(wres_bar, 0); tc_fence_after(); }
     // next W block: resident address or ring slot (returns hi address; lo = hi + plane).  which: 0 = W1, 1 = W2 hidden part, 2 = W2 x part
@@ -182,8 +185,10 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
     // GEMM2 of the it-th tile: hidden tile (shared memory) [+ raw x blocks of the conv shortcut] -> acc2
     auto gemm2 = [&](int it) {
         const int hb = p.dbl ? (it & 1) : 0;
+        const int b2 = p.pp ? (it & 1) : 0;
+        const uint32_t acc2 = tmem_base + p.acc2_col + b2 * p.acc2_stride;
         mbar_wait(&h_ready[hb], p.dbl ? ((it >> 1) & 1) : (it & 1));
-        mbar_wait(acc_free, (it & 1) ^ 1);  // epilogue 2 of the previous tile has drained acc2
+        mbar_wait(&acc_free[b2], (p.pp ? ((it >> 1) & 1) : (it & 1)) ^ 1);  // epilogue 2 of the previous user of this acc2 buffer has drained it
         tc_fence_after();
         const uint32_t hbase = h_u + hb * p.h_stage_bytes;
         uint32_t acc = 0;
@@ -221,7 +226,7 @@ __device__ __forceinline__ void mma_role(const RuParams& p, uint8_t* a_ring, uin
                 if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
             }
         }
-        if (leader) umma_commit(acc2_full);
+        if (leader) umma_commit(&acc2_full[b2]);
         __syncwarp();
     };
     // Issue order (the producers follow the same order):  G1(0) | G1(1) G2(0) | G1(2) G2(1) | ...   when double-buffered,
@@ -287,9 +292,9 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     uint64_t* w_empty = w_full + MAX_W_STAGES;
     uint64_t* acc1_full = w_empty + MAX_W_STAGES;  // [2]
     uint64_t* h_ready = acc1_full + 2;             // [2]
-    uint64_t* acc2_full = h_ready + 2;
-    uint64_t* acc_free = acc2_full + 1;
-    uint64_t* wres_bar = acc_free + 1;
+    uint64_t* acc2_full = h_ready + 2;             // [2]
+    uint64_t* acc_free = acc2_full + 2;            // [2]
+    uint64_t* wres_bar = acc_free + 2;
     uint64_t* io_ready = wres_bar + 1;   // this tile's skip input has landed in the staging buffer
     uint64_t* out_free = io_ready + 1;   // the previous tile's stores have read the output staging buffers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
@@ -319,9 +324,11 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             mbar_init(&e_empty[i], 1);
         }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&h_ready[i], EPI_WARPS); }
-        mbar_init(acc2_full, 1);
-        mbar_init(acc_free, EPI_WARPS);
+        const int epi_n = p.pp ? EPI_WARPS / 2 : EPI_WARPS;   // warps that hand over one tile
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc1_full[i], 1); mbar_init(&h_ready[i], epi_n);
+            mbar_init(&acc2_full[i], 1); mbar_init(&acc_free[i], epi_n);
+        }
         mbar_init(wres_bar, 1);
         mbar_init(io_ready, 1);
         mbar_init(out_free, 1);
@@ -519,7 +526,9 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
     } else {
         // ================================================================= epilogue warps
         const int quarter = warp & 3;
-        const int slot = (warp - FIRST_EPI_WARP) >> 2;  // 0 .. EPI_WARPS/4 - 1
+        const int grp = p.pp ? (warp - FIRST_EPI_WARP) >> 3 : 0;           // ping-pong: warps 3-10 take the even tiles, 11-18 the odd ones
+        const int nslots = p.pp ? EPI_WARPS / 8 : EPI_WARPS / 4;            // warps per TMEM lane quarter working on one tile
+        const int slot = ((warp - FIRST_EPI_WARP) >> 2) & (nslots - 1);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int c1 = p.ch / 16, c2 = p.cout / 16;
         const int units_per_row = p.bkh / 8;                       // 16-byte units per hidden-tile row: 8 / 4 / 2
@@ -535,7 +544,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             const uint32_t acc1 = lane_addr + ab * p.acc1_stride;
             int g = 0, c = slot;
             while (c >= c1) { c -= c1; ++g; }
-            for (int item = slot; item < p.G * c1; item += EPI_WARPS / 4) {
+            for (int item = slot; item < p.G * c1; item += nslots) {
                 uint32_t v[16];
                 tmem_ld16(acc1 + g * p.ch + c * 16, v);
                 const int row = g * TILE_M + quarter * 32 + lane;  // row of the hidden tile
@@ -563,7 +572,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                     *reinterpret_cast<uint4*>(rowp + p.h_plane_bytes + (((u0) ^ xr) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     *reinterpret_cast<uint4*>(rowp + p.h_plane_bytes + (((u0 + 1) ^ xr) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
-                c += EPI_WARPS / 4;
+                c += nslots;
                 while (c >= c1) { c -= c1; ++g; }
             }
             tc_fence_before();
@@ -639,13 +648,13 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             }
             mbar_wait(io_ready, it & 1);   // this tile's skip input has landed
             mbar_wait(out_free, it & 1);
-            mbar_wait(acc2_full, it & 1);
+            mbar_wait(&acc2_full[0], it & 1);
             tc_fence_after();
             uint8_t* y_s = io_s + (size_t)p.io_y_off * p.io_plane_bytes;
             uint8_t* act_s = io_s + (size_t)p.io_act_off * p.io_plane_bytes;
             int g = 0, c = slot;
             while (c >= c2) { c -= c2; ++g; }
-            for (int item = slot; item < p.G * c2; item += EPI_WARPS / 4) {
+            for (int item = slot; item < p.G * c2; item += nslots) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + p.acc2_col + g * p.cout + c * 16, v);
                 const int row = quarter * 32 + lane;          // row inside the 128-row piece g
@@ -654,7 +663,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                 const int xr = (row >> io_xshift) & (io_units - 1);
                 const uint32_t off = (uint32_t)kb * p.io_blk_bytes + (uint32_t)g * io_piece_bytes + (uint32_t)row * io_row_bytes;
                 const uint32_t o0 = off + (((u0) ^ xr) << 4), o1 = off + (((u0 + 1) ^ xr) << 4);
-                c += EPI_WARPS / 4;
+                c += nslots;
                 while (c >= c2) { c -= c2; ++g; }
                 uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, l0 = r0, l1 = r0;
                 if (has_res) {
@@ -697,7 +706,7 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_free);     // acc2 drained: GEMM2 of the next tile may start
+            if (lane == 0) mbar_arrive(&acc_free[0]); // acc2 drained: GEMM2 of the next tile may start
             fence_proxy_async();                      // generic-proxy writes of the staged tiles -> visible to the TMA stores
             asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // every epilogue warp has finished the tile
             if (io_leader) {
@@ -714,18 +723,20 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             int g = 0, c = slot;
             while (c >= c2) { c -= c2; ++g; }
             if (has_res && slot < p.G * c2) fetch_res(b, mg, g, c);
-            mbar_wait(acc2_full, it & 1);
+            const int b2 = p.pp ? (it & 1) : 0;
+            const uint32_t acc2 = lane_addr + p.acc2_col + b2 * p.acc2_stride;
+            mbar_wait(&acc2_full[b2], p.pp ? ((it >> 1) & 1) : (it & 1));
             tc_fence_after();
-            for (int item = slot; item < p.G * c2; item += EPI_WARPS / 4) {
+            for (int item = slot; item < p.G * c2; item += nslots) {
                 uint32_t v[16];
-                tmem_ld16(lane_addr + p.acc2_col + g * p.cout + c * 16, v);
+                tmem_ld16(acc2 + g * p.cout + c * 16, v);
                 const int m = (mg * p.G + g) * TILE_M + quarter * 32 + lane;
                 const int col = c * 16;
                 const long long flat = (long long)m * p.cout + col;
-                c += EPI_WARPS / 4;
+                c += nslots;
                 while (c >= c2) { c -= c2; ++g; }
                 const uint4 rcur[4] = {rnext[0], rnext[1], rnext[2], rnext[3]};
-                if (has_res && item + EPI_WARPS / 4 < p.G * c2) fetch_res(b, mg, g, c);
+                if (has_res && item + nslots < p.G * c2) fetch_res(b, mg, g, c);
                 tmem_ld_wait();
                 if (m >= p.m_rows) continue;
                 float o[16];
@@ -742,10 +753,12 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_free);
+            if (lane == 0) mbar_arrive(&acc_free[b2]);
         };
         // same order as the MMA warp: epilogue 1 of tile i+1 runs before epilogue 2 of tile i when double-buffered
-        if (p.dbl) {
+        if (p.pp) {
+            for (int it = grp; it < my_tiles; it += 2) { epi1(it); epi2(it); }   // this group's tiles; the other group is a phase away
+        } else if (p.dbl) {
             if (my_tiles > 0) epi1(0);
             for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) epi1(it + 1);
@@ -834,7 +847,8 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     const int io_res = (d->res ? 1 : 0) + (d->res_lo ? 1 : 0), io_y = (d->y ? 1 : 0) + (d->y_lo ? 1 : 0), io_a = (d->y_act ? 1 : 0) + (d->y_act_lo ? 1 : 0);
     const int io_planes = io_res + io_y + io_a;
     const int bko = d->cout % 64 == 0 ? 64 : (d->cout % 32 == 0 ? 32 : 16);
-    bool use_io = d->io_stage >= 0 && !raw;
+    const bool want_pp = d->dbl_hint == 2 && !raw;   // ping-pong epilogue groups (the hint 2 = double-buffered + ping-pong)
+    bool use_io = d->io_stage >= 0 && !raw && !want_pp;
     auto search = [&](int g_only, int bk_only, int bkh_only, bool use_hint) -> bool {
     // pass 0: double-buffered hidden tile / acc1 with deep rings; pass 1: double-buffered, any rings; pass 2: single-buffered
     for (int pass = 0; pass < 3; ++pass)
@@ -843,7 +857,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
             if (d->cin % bk || d->ch % bkh) continue;
             if ((bk_only > 0 && bk != bk_only) || (bkh_only > 0 && bkh != bkh_only)) continue;
             const int dbl = pass < 2 ? 1 : 0;
-            if (use_hint && d->dbl_hint >= 0 && dbl != d->dbl_hint) continue;
+            if (use_hint && d->dbl_hint >= 0 && dbl != (d->dbl_hint ? 1 : 0)) continue;
             const int chunks1 = d->cin / bk, hblocks = d->ch / bkh, xchunks = has_x ? d->cin / bk : 0;
             const int nkb1 = d->taps * chunks1;
             const uint32_t w1_kb = round_up((uint32_t)d->ch * bk * 2, 1024), w2h_kb = round_up((uint32_t)d->cout * bkh * 2, 1024),
@@ -853,7 +867,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
             for (int G : {4, 2, 1}) {
                 if (g_only > 0 && G != g_only) continue;
                 if (use_hint && d->g_hint > 0 && G != d->g_hint) continue;
-                const int need_cols = G * ((1 + dbl) * d->ch + d->cout);
+                const int need_cols = G * ((1 + dbl) * d->ch + (1 + (dbl && want_pp ? 1 : 0)) * d->cout);
                 if (need_cols > 512) continue;
                 if (!(use_hint && d->g_hint > 0) && G > 1 && (m_tiles / G) * d->batch < 2LL * sms) continue;
                 const int R = G * TILE_M + halo;
@@ -909,7 +923,7 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
                 p.w2x_res_off = p.w2h_res_off + (uint32_t)hblocks * w2h_kb * pl2;
                 p.w_area_bytes = (uint32_t)w_area;
                 p.h_blk_bytes = h_blk; p.h_plane_bytes = h_plane; p.h_stage_bytes = (uint32_t)h_stage;
-                p.dbl = dbl; p.acc1_stride = (uint32_t)G * d->ch;
+                p.dbl = dbl; p.pp = (dbl && want_pp) ? 1 : 0; p.acc1_stride = (uint32_t)G * d->ch; p.acc2_stride = (uint32_t)G * d->cout;
                 p.tmem_cols = cols; p.acc2_col = (uint32_t)G * d->ch * (1 + dbl);
                 return true;
             }

@@ -73,7 +73,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (AC_MBAR_SUSPEND_NS > 0 ? (1u << 17) : (1u << 24))) __trap();   // ~2.7 s either way (20 us / ~160 ns per failed poll)
     }
 }
 

@@ -294,7 +294,7 @@ class DAC(Codec):
             variants = [("unfused", unfused)]
             if 2 * C <= 512:
                 # io: 1 = skip input / outputs staged in shared memory and moved by TMA, -1 = direct loads / stores (bit-identical)
-                fv = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (2, 1) for dbl in (1, 0) for io in (-1, 1)]
+                fv = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (2, 1) for dbl in (2, 1, 0) for io in (-1, 1) if not (dbl == 2 and io == 1)]
                 variants = fv if enc else fv + variants
             tc.autotune(("dac_unit", B, L, C, d, last, x.lo is not None, xs.lo is not None, enc, xs.f16, W7.planes, W1.planes), variants)
             x, xs = y, ys

@@ -274,7 +274,7 @@ class Encodec(Codec):
                                          io_stage=io, name="resblock_tc")
 
         # io: 1 = outputs staged in shared memory and sent out by TMA stores, -1 = direct stores (bit-identical results)
-        variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (1, 0) for io in (-1, 1)]
+        variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (2, 1, 0) for io in (-1, 1) if not (dbl == 2 and io == 1)]
         if FUSED_MAX_CH is None:
             variants.append(("unfused", unfused))
         elif C > FUSED_MAX_CH:

@@ -233,7 +233,7 @@ class Mimi(Codec):
         # must not depend on the batch it is tuned in; the tuner only picks the tile grouping / buffering (bit-identical)
         variants = [("unfused", unfused)]
         if C <= 256:
-            variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (1, 0) for io in (-1, 1)]
+            variants = [(f"fused_g{g}_d{dbl}_io{io}", fused(g, dbl, io)) for g in (4, 2, 1) for dbl in (2, 1, 0) for io in (-1, 1) if not (dbl == 2 and io == 1)]
         tc.autotune(("mimi_resblock", B, L, C, x.lo is not None, hs, x.f16, Wk3.planes, Wk1.planes), variants)
 
     def _tc_transformer(self, layers, tws, h, pol):

@@ -265,7 +265,9 @@ typedef struct ac_resunit_tc_desc {
     void* y; void* y_lo; void* y_act; void* y_act_lo;
     int64_t y_bstride, y_act_bstride;
     int32_t batch, m_rows, bk, g_hint, grid_hint;
-    int32_t dbl_hint;                      /* -1 automatic; 0 / 1: single / double-buffered hidden tile and first accumulator */
+    int32_t dbl_hint;                      /* -1 automatic; 0 / 1: single / double-buffered hidden tile and first accumulator; 2: double-
+                                              buffered with the second accumulator doubled too and the epilogue warps in two groups that
+                                              take alternate tiles (ping-pong; needs G*(2*ch + 2*cout) <= 512 tensor-memory columns) */
     /* raw mode (act0 != AC_ACT_NONE): `a` is the RAW input and the kernel applies the unit's input activation act0 (ELU, or
        Snake with alpha0[cin]) on chip, block by block, before GEMM1 -- the producer layer then writes one tensor instead of a
        raw and an activated copy.  e_split: the activated operand carries a lo plane.  x_from_a: the conv shortcut reads the raw

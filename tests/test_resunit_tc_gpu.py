@@ -204,3 +204,31 @@ def test_dac_residual_unit_raw_mode(C, L, B, dil):
     assert torch.isfinite(got).all() and torch.isfinite(got_s).all()
     assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
     assert (got_s - ref_s).abs().max().item() <= 3e-2 * max(1.0, ref_s.abs().max().item())
+
+
+@pytest.mark.parametrize("C,L,B,dil,g", [(64, 4000 + 37, 5, 9, 1), (64, 3000, 3, 1, 2), (96, 2500, 2, 3, 1), (128, 1500, 2, 9, 1)])
+def test_ping_pong_epilogue_groups_bit_identical(C, L, B, dil, g):
+    """dbl_hint=2: second accumulator double-buffered too, the sixteen epilogue warps in two groups that take alternate tiles.
+    Same contraction blocks and product order as every other tiling of the shape, so the outputs must be bit-identical to the
+    default launch -- with more tiles than CTAs (grid_hint) so that both groups and both buffers of every barrier are exercised."""
+    gen = torch.Generator().manual_seed(C + dil)
+    x = torch.randn(B, L, C, generator=gen)
+    al1, al2, al3 = (torch.rand(C, generator=gen) + 0.5 for _ in range(3))
+    w7 = torch.randn(C, C, 7, generator=gen) * (7 * C) ** -0.5
+    w1 = torch.randn(C, C, generator=gen) * C ** -0.5
+    b7, b1 = torch.randn(C, generator=gen) * 0.1, torch.randn(C, generator=gen) * 0.1
+    xs_act, _ = _act_from(_snake(x, al1), False)
+    x_act, _ = _act_from(x, True)
+    W1, W2 = TcWeights(w7.permute(0, 2, 1).reshape(C, -1), b7), TcWeights(w1, b1)
+    for W in (W1, W2):
+        W.apply(lambda t: t.to(DEV))
+    outs = []
+    for dbl, grid in ((-1, 0), (2, 7), (2, 0)):
+        y, ys = Act(B, L, C, DEV, split=True), Act(B, L, C, DEV)
+        tc.resunit_tc(W1, W2, Src(xs_act, taps=7, dilation=dil, shift=-3 * dil), L, res=x_act, y=y, y_act=ys, act1=ops.ACT_SNAKE,
+                      alpha1=al2.to(DEV), act2=ops.ACT_SNAKE, alpha2=al3.to(DEV), g_hint=g if dbl == 2 else 0, dbl_hint=dbl, grid_hint=grid)
+        torch.cuda.synchronize()
+        outs.append((y.data().clone(), y.lo[:, :L].clone(), ys.data().clone()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
