@@ -481,10 +481,10 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                 uint8_t* dst = e_ring + (size_t)stage * p.e_stage_bytes;
                 for (int u = t; u < units; u += 32 * XF_WARPS) {
                     const uint4 h = *reinterpret_cast<const uint4*>(src + (size_t)u * 16);
-                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(hp[i]); v[2 * i + 1] = __high2float(hp[i]); }
+                    for (int i = 0; i < 4; ++i) { const float2 f = unpack16(hw[i], p.f16 != 0); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
                     if (p.a_has_lo) {
                         const uint4 l = *reinterpret_cast<const uint4*>(src + p.a_plane_bytes + (size_t)u * 16);
                         const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
@@ -509,9 +509,9 @@ resunit_tc_kernel(const __grid_constant__ RuMaps maps, const __grid_constant__ R
                             }
                         }
                     }
-                    const uint4 q = pack8(v);
+                    const uint4 q = pack8(v, p.f16 != 0);
                     *reinterpret_cast<uint4*>(dst + (size_t)u * 16) = q;
-                    if (p.e_split) *reinterpret_cast<uint4*>(dst + p.e_plane_bytes + (size_t)u * 16) = pack_lo(v, q);
+                    if (p.e_split) *reinterpret_cast<uint4*>(dst + p.e_plane_bytes + (size_t)u * 16) = pack_lo(v, q, p.f16 != 0);
                 }
                 fence_proxy_async();  // generic-proxy stores of the activated block -> visible to tcgen05.mma
                 __syncwarp();
@@ -823,7 +823,6 @@ extern "C" int ac_resunit_tc(const ac_resunit_tc_desc* d, void* stream) {
     const int w1_split = d->w1_split ? 1 : 0, w2_split = d->w2_split ? 1 : 0, h_split = d->h_split ? 1 : 0;
     const int f16 = (d->fmt & AC_FMT_A_F16) ? 1 : 0, w1_hib = (d->fmt & AC_FMT_W_HIB) ? 1 : 0, w2_hib = (d->fmt & AC_FMT_W2_HIB) ? 1 : 0;
     AC_REQUIRE(f16 || !(w1_hib | w2_hib), "ac_resunit_tc: the extra bf16(W) planes only exist for fp16 operands");
-    AC_REQUIRE(!f16 || d->act0 == AC_ACT_NONE, "ac_resunit_tc: raw mode (act0) is bf16 only");
     AC_REQUIRE(!f16 || ((!d->a_lo || w1_hib) && (!(h_split || (d->x && d->x_lo)) || w2_hib)),
                "ac_resunit_tc: fp16 operands with a lo plane need the bf16(W) plane of that GEMM");
     const int pl1 = 1 + w1_split + w1_hib, pl2 = 1 + w2_split + w2_hib;

@@ -15,10 +15,12 @@ __all__ = ["Encodec"]
 RATIOS = (8, 5, 4, 2)  # facebook/encodec_24khz upsampling_ratios (HF/encodec/configuration_encodec.py)
 SPLIT_MIN_CH = 128     # precision="bf16": activations with >= this many channels travel as (hi, lo) bf16 pairs (DESIGN.md,
                        # precision); precision="exact": every ENCODER activation does (three products per MAC)
-RAW_MAX_CH = 0         # residual blocks with <= this many channels take RAW x and apply their input ELU on chip (raw mode of
-                       # ac_resunit_tc: the producer layer writes one tensor instead of a raw and an activated copy).  Measured at
-                       # 64: producers 25-35 % faster, but the blocks themselves 1.8x slower (raw + activated blocks halve the ring
-                       # depth that fits shared memory) -- a net loss of 0.8 ms per step, so it is off
+RAW_MAX_CH = int(__import__("os").environ.get("AC_RAW_MAX_CH", "0"))   # residual blocks with <= this many channels take RAW x and
+                       # apply their input ELU on chip (raw mode of ac_resunit_tc: the producer layer writes one tensor instead of a raw
+                       # and an activated copy).  Off: measured twice a net loss.  Round 1 (bf16, 64 channels): producers 25-35 %
+                       # faster, blocks 1.8x slower.  Round 2 (all formats, 32 channels): first layer 0.67 -> 0.39 ms (exact) /
+                       # 0.40 -> 0.30 ms (fp16) but the block 0.95 -> 1.57 ms / 0.64 -> 0.93 ms -- the transform stage sits between
+                       # TMA and MMA on a ring the extra planes shrink to two stages
 FUSED_MAX_CH = 64      # residual blocks with <= this many channels run as ONE fused launch (hidden tile on chip), wider ones as two
                        # tap-GEMM launches (measured faster at 128 / 256 channels).  A rule, not a timing: the two forms group
                        # the fp32 accumulation differently, so the choice must not depend on the batch size.  None = let the
