@@ -21,8 +21,10 @@ RAW_MAX_CH = int(__import__("os").environ.get("AC_RAW_MAX_CH", "0"))   # residua
                        # faster, blocks 1.8x slower.  Round 2 (all formats, 32 channels): first layer 0.67 -> 0.39 ms (exact) /
                        # 0.40 -> 0.30 ms (fp16) but the block 0.95 -> 1.57 ms / 0.64 -> 0.93 ms -- the transform stage sits between
                        # TMA and MMA on a ring the extra planes shrink to two stages
-FUSED_MAX_CH = 64      # residual blocks with <= this many channels run as ONE fused launch (hidden tile on chip), wider ones as two
-                       # tap-GEMM launches (measured faster at 128 / 256 channels).  A rule, not a timing: the two forms group
+FUSED_MAX_CH = int(__import__("os").environ.get("AC_FUSED_MAX_CH", "64"))   # residual blocks with <= this many channels run as ONE fused launch (hidden tile on chip), wider ones as two
+                       # tap-GEMM launches.  Re-measured in round 2 (after the epilogue diet and the ping-pong groups): at 128 channels fused is
+                       # 0.35 vs 0.40 ms (fp16) / 0.76 vs 0.85 ms (exact) -- 0.07 ms of a 17.4 ms step in the bench loop, not worth
+                       # re-grouping the encoder's accumulation -- and at 256 it loses (0.65-0.80 vs 0.48 ms exact).  A rule, not a timing: the two forms group
                        # the fp32 accumulation differently, so the choice must not depend on the batch size.  None = let the
                        # tuner time one against the other (scripts/tune_report.py)
 _VALID_BW = (1.5, 3.0, 6.0, 12.0, 24.0)
