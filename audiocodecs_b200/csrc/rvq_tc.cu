@@ -20,6 +20,7 @@
 //     emitted code is the fp32 argmin wherever the tensor-core ranking has the true winner in its top 2; the winner is
 //     subtracted from the residual in place and the operand planes are re-split for the next stage.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -30,14 +31,15 @@ using namespace sm100;
 
 constexpr int TM = 128;           // frames per tile
 constexpr int CHUNK = 64;         // codes per ring block / per MMA N
-constexpr int GROUP = 128;        // codes per TMEM distance buffer
+constexpr int GROUP_MAX = 128;    // codes per TMEM distance buffer: 128 (one CTA per SM, 512 TMEM columns), or 64 with D = 128 --
+                                  // residual 128 + 2 x 64 distance columns = 256: TWO CTAs share an SM and one CTA's serial tail
+                                  // (candidate merge, exact re-score, subtract, re-split) runs under the other's distance GEMM
 constexpr int MAX_RING = 10;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t PLANE_KB_BYTES = TM * 128;             // one [128 rows x 64] SW128 block of an operand plane: 16 KB
 constexpr uint32_t E_BLOCK_BYTES = CHUNK * 128;           // [64 codes x 64 dims] SW128: 8 KB
 constexpr uint32_t RING_STAGE_BYTES = 2 * E_BLOCK_BYTES;  // one k-block of a chunk: E_hi, E_lo = 16 KB
-constexpr uint32_t R_COL = 256;                            // residual columns start after the two distance buffers
 constexpr int XCH = 8;                                     // floats exchanged per (frame, half)
 constexpr int MAX_CODES = 2048;
 
@@ -82,9 +84,12 @@ __device__ __forceinline__ float ref_score(float xn, float dot, float en, int me
     return -sqrtf(fmaxf((xn + en) - 2.f * dot, 0.f));          // cdist, HF/mimi:1200
 }
 
-template <int D>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int D, int GROUP>
+__global__ void __launch_bounds__(THREADS, GROUP == 64 ? 2 : 1)
 rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p) {
+    constexpr uint32_t R_COL = 2 * GROUP;            // residual columns start after the two distance buffers
+    constexpr uint32_t TMEM_COLS = (2 * GROUP + D) <= 256 ? 256 : 512;
+    constexpr int HG = GROUP / 2;                    // codes of a distance buffer scanned by one thread of a frame
     constexpr int KB = D / 64;                       // k-blocks of 64 dims
     constexpr int HD = D / 2;                        // dims owned by one thread of a frame
     constexpr uint32_t A_PLANE_BYTES = KB * PLANE_KB_BYTES;
@@ -94,7 +99,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
     uint8_t* a_lo = a_hi + A_PLANE_BYTES;
     uint8_t* ring = a_lo + A_PLANE_BYTES;
     float* en_s = reinterpret_cast<float*>(ring + (size_t)p.ring * RING_STAGE_BYTES);  // [n_codes <= 2048]
-    float* xch = en_s + MAX_CODES;                          // [TM][2][XCH] exchange between the two halves of a frame
+    float* xch = en_s + p.n_codes;                          // [TM][2][XCH] exchange between the two halves of a frame
     uint64_t* bars = reinterpret_cast<uint64_t*>(xch + TM * 2 * XCH);
     uint64_t* full = bars;                      // [MAX_RING]
     uint64_t* empty = bars + MAX_RING;          // [MAX_RING]
@@ -114,7 +119,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
         mbar_init(a_ready, EPI_WARPS);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -260,8 +265,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
                     mbar_wait(&tfull[buf], (gcount >> 1) & 1);
                     tc_fence_after();
 #pragma unroll 2
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const int col = half * 64 + cc * 16;
+                    for (int cc = 0; cc < HG / 16; ++cc) {
+                        const int col = half * HG + cc * 16;
                         uint32_t v[16];
                         tmem_ld16(lane_addr + buf * GROUP + col, v);
                         const float4* enp = reinterpret_cast<const float4*>(en + g * GROUP + col);
@@ -271,7 +276,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
                             const float4 t = enp[q];
                             e[4 * q] = xn + t.x; e[4 * q + 1] = xn + t.y; e[4 * q + 2] = xn + t.z; e[4 * q + 3] = xn + t.w;
                         }
-                        const uint32_t lbase = (uint32_t)(g * 64 + cc * 16);
+                        const uint32_t lbase = (uint32_t)(g * HG + cc * 16);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -287,7 +292,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
                 // ---- merge the two halves' candidates -> the frame's top 2 (truncated distance, then GLOBAL index)
-                auto glob = [&](uint32_t kk, int h) { const int l = (int)(kk & 1023u); return (l >> 6) * GROUP + h * 64 + (l & 63); };
+                auto glob = [&](uint32_t kk, int h) { const int l = (int)(kk & 1023u); return (l / HG) * GROUP + h * HG + (l % HG); };
                 float v1 = -__uint_as_float(k1 & 0xFFFFFC00u), v2 = -__uint_as_float(k2 & 0xFFFFFC00u);  // larger is better
                 int i1 = glob(k1, half), i2 = glob(k2, half);
                 my_x[1] = v1; my_x[2] = __int_as_float(i1); my_x[3] = v2; my_x[4] = __int_as_float(i2);
@@ -366,7 +371,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap emap, const RvqParams p
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -374,26 +379,28 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int D>
+template <int D, int GROUP>
 int launch(const CUtensorMap& emap, RvqParams p, cudaStream_t stream) {
+    constexpr int per_sm = GROUP == 64 ? 2 : 1;
     const size_t a_planes = 2 * (size_t)(D / 64) * PLANE_KB_BYTES;
-    const size_t fixed = 1024 + a_planes + MAX_CODES * 4 + TM * 2 * XCH * 4 + (2 * MAX_RING + 5) * 8 + 16;
-    int ring = (int)((227 * 1024 - fixed) / RING_STAGE_BYTES);
+    const size_t fixed = 1024 + a_planes + (size_t)p.n_codes * 4 + TM * 2 * XCH * 4 + (2 * MAX_RING + 5) * 8 + 16;
+    const size_t budget = per_sm == 2 ? 113 * 1024 : 227 * 1024;
+    int ring = (int)((budget - fixed) / RING_STAGE_BYTES);
     if (ring > MAX_RING) ring = MAX_RING;
     if (ring < 2) { ac::set_error("ac_rvq_encode_tc: shared memory"); return -1; }
     p.ring = ring;
     const size_t smem = fixed + (size_t)ring * RING_STAGE_BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rvq_encode_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rvq_encode_tc_kernel<D, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
         if (e != cudaSuccess) { ac::set_error("ac_rvq_encode_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = p.tiles < sms ? p.tiles : sms;
-    rvq_encode_tc_kernel<D><<<grid, THREADS, smem, stream>>>(emap, p);
+    const int grid = p.tiles < per_sm * sms ? p.tiles : per_sm * sms;
+    rvq_encode_tc_kernel<D, GROUP><<<grid, THREADS, smem, stream>>>(emap, p);
     return ac::finish_launch("ac_rvq_encode_tc");
 }
 
@@ -406,8 +413,8 @@ extern "C" int ac_rvq_encode_tc(const float* x, const void* cb_split_bf16, const
     AC_REQUIRE(x && cb_split_bf16 && codebooks && cb_norm && codes_out, "ac_rvq_encode_tc: null pointer");
     AC_REQUIRE(rows > 0 && stages > 0 && stage0 >= 0 && stage0 + stages <= stages_total, "ac_rvq_encode_tc: bad stage range");
     AC_REQUIRE(dim == 128 || dim == 256, "ac_rvq_encode_tc: dim %d (128 or 256)", dim);
-    AC_REQUIRE(n_codes % GROUP == 0 && n_codes >= 2 * GROUP && n_codes <= MAX_CODES,
-               "ac_rvq_encode_tc: n_codes %d must be a multiple of %d in [%d, %d]", n_codes, GROUP, 2 * GROUP, MAX_CODES);
+    AC_REQUIRE(n_codes % GROUP_MAX == 0 && n_codes >= 2 * GROUP_MAX && n_codes <= MAX_CODES,
+               "ac_rvq_encode_tc: n_codes %d must be a multiple of %d in [%d, %d]", n_codes, GROUP_MAX, 2 * GROUP_MAX, MAX_CODES);
     AC_REQUIRE(metric == 0 || metric == 1, "ac_rvq_encode_tc: metric %d", metric);
     AC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)codebooks & 15) == 0 && ((uintptr_t)cb_split_bf16 & 15) == 0,
                "ac_rvq_encode_tc: pointers must be 16-byte aligned");
@@ -436,5 +443,13 @@ extern "C" int ac_rvq_encode_tc(const float* x, const void* cb_split_bf16, const
     p.tiles = (int)((rows + TM - 1) / TM);
     p.metric = metric;
     p.lo_row0 = stages_total * n_codes;
-    return dim == 128 ? launch<128>(emap, p, (cudaStream_t)stream) : launch<256>(emap, p, (cudaStream_t)stream);
+    // D = 128: two CTAs per SM (64-code distance buffers) once there is more than one tile per SM to overlap; AC_RVQ_PAIR=0/1 forces
+    static int pair = -1;
+    if (pair < 0) { const char* env = getenv("AC_RVQ_PAIR"); pair = env ? atoi(env) : 2; }
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool use_pair = dim == 128 && (pair == 1 || (pair == 2 && p.tiles > sms));
+    if (use_pair) return launch<128, 64>(emap, p, (cudaStream_t)stream);
+    return dim == 128 ? launch<128, 128>(emap, p, (cudaStream_t)stream) : launch<256, 128>(emap, p, (cudaStream_t)stream);
 }

@@ -17,8 +17,8 @@ prec = os.environ.get("AC_PRECISION", "exact")
 if os.environ.get("AC_TUNE_FUSION"):
     from audiocodecs_b200 import encodec as _enc
     _enc.FUSED_MAX_CH = None
-if which == "encodec":
-    codec, sr = A.Encodec(24000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0), precision=prec), 24000
+if which in ("encodec", "encodec32"):
+    codec, sr = A.Encodec(24000, 24000, num_codebooks=32 if which == "encodec32" else 8, state_dict=weights.encodec_state_dict(0), precision=prec), 24000
 elif which == "dac":
     codec, sr = A.DAC(44100, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision=prec, split_min_ch=smin), 44100
 else:
