@@ -20,6 +20,7 @@
 // fire-and-forget global stores issued one step late, off the critical path.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -32,8 +33,7 @@ constexpr int CL = 16;        // CTAs per cluster
 constexpr int HID = 512;      // hidden size (EnCodec)
 constexpr int UPC = HID / CL; // 32 units per CTA
 constexpr int NB = 16;        // clips per cluster (UMMA N)
-constexpr int EPI_WARPS = 8;   // two per TMEM lane quarter: each takes 8 of the 16 clips
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+// epilogue warps (template parameter EW): 8 (two per TMEM lane quarter, 8 clips each) or 16 (four per quarter, 4 clips each)
 constexpr uint32_t B_BYTES = NB * HID * 2;          // 16384 per parity
 constexpr uint32_t SLICE_BYTES = NB * UPC * 2;      // 1024: one CTA's 32 units of all 16 clips
 constexpr uint32_t GS_FLOATS = 4 * UPC * 17;        // gate exchange, padded
@@ -78,7 +78,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
     return r;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+template <int EW>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); }  // the epilogue warps
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -122,8 +127,10 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                  ::"r"(dst_cluster), "r"(src_local), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
+    constexpr int THREADS = 64 + 32 * EW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* b_s = smem;                         // h operand: 2 parities x 16 KB, un-swizzled K-major core matrices
@@ -209,8 +216,8 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         }
     } else if (warp >= 2) {
         // ======================================================== epilogue: 256 threads
-        constexpr int HC = NB / 2;         // clips per thread in the activation phase (this warp's half of the columns)
-        constexpr int CPT = NB / EPI_WARPS;  // clips per thread in the cell update
+        constexpr int HC = NB / (EW / 4);  // clips per thread in the activation phase (this warp's share of the 16 columns)
+        constexpr int CPT = NB / EW;       // clips per thread in the cell update
         const int ew = warp - 2;           // 0..7
         const int g = warp & 3;            // TMEM lane quarter == gate index (rows g*32 + u)
         const int ch = ew >> 2;            // which 8 clips this warp activates
@@ -254,7 +261,8 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         };
         // destinations of this CTA's slice: every warp pushes to two peers (operand buffer + 1 KB * rank, and the peer's
         // h_ready barrier); spreading the 16 bulk copies over the warps keeps each warp's issue loop short
-        const uint32_t dst_rank = (uint32_t)(ew * 2 + (lane & 1));
+        constexpr int PEERS = CL / EW;     // peers each warp pushes the slice to (2 with 8 warps, 1 with 16)
+        const uint32_t dst_rank = (uint32_t)(ew * PEERS + (lane % PEERS));
         const uint32_t peer_b = map_to_cta(smem_u32(b_s) + rank * SLICE_BYTES, dst_rank);
         const uint32_t peer_bar = map_to_cta(smem_u32(&h_ready[0]), dst_rank);
         load_pre(0);
@@ -269,7 +277,8 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             tc_fence_after();
             if (dbg) p.dbg[t * 8 + 1] = clock64();
             uint32_t v[HC];
-            tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16) + ch * HC, v);
+            if constexpr (HC == 8) tmem_ld8(tmem_base + ((uint32_t)(g * 32) << 16) + ch * HC, v);
+            else tmem_ld4(tmem_base + ((uint32_t)(g * 32) << 16) + ch * HC, v);
             tmem_ld_wait();
             tc_fence_before();
             if (g == 2) {  // warp-uniform: the g gate is tanh, i/f/o are sigmoids
@@ -279,7 +288,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
 #pragma unroll
                 for (int b = 0; b < HC; ++b) gs[(g * UPC + u) * 17 + ch * HC + b] = fast_sigmoid(__uint_as_float(v[b]) + pre_cur[b]);
             }
-            epi_bar_sync();
+            epi_bar_sync<EW>();
             if (dbg) p.dbg[t * 8 + 2] = clock64();
             const int npar = (t + 1) & 1;
             uint8_t* hsl = hs + npar * SLICE_BYTES;
@@ -299,8 +308,8 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             if (t + 1 < p.steps) {
                 fence_proxy_async();      // this thread's generic-proxy stores to hs (shared::cta only: a full proxy fence would also
                                           // wait for the deferred global stores) -> visible to the bulk-copy (async) proxy
-                epi_bar_sync();           // slice complete (and gs reads finished)
-                if (lane < 2) bulk_copy_to_peer(peer_b + npar * B_BYTES, smem_u32(hsl), SLICE_BYTES, peer_bar + npar * 8);
+                epi_bar_sync<EW>();           // slice complete (and gs reads finished)
+                if (lane < PEERS) bulk_copy_to_peer(peer_b + npar * B_BYTES, smem_u32(hsl), SLICE_BYTES, peer_bar + npar * 8);
                 if (dbg) p.dbg[t * 8 + 4] = clock64();
             }
         }
@@ -320,19 +329,19 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
 
 // Diagnostic: how many clusters of `cluster_size` CTAs of this kernel the device can hold at once (cudaOccupancyMaxActiveClusters).
 extern "C" int ac_lstm_tc_max_clusters(int32_t cluster_size, int32_t smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute((const void*)lstm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)lstm_tc_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc_max_clusters: %s", cudaGetErrorString(e)); return -1; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cluster_size * 16);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(64 + 32 * 8);
     cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, (const void*)lstm_tc_kernel, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, (const void*)lstm_tc_kernel<8>, &cfg);
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc_max_clusters: %s", cudaGetErrorString(e)); cudaGetLastError(); return -1; }
     return n;
 }
@@ -351,7 +360,7 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     const int nbv = NB;
     static bool configured = false;
     if (!configured) {
-        for (const void* fn : {(const void*)lstm_tc_kernel}) {
+        for (const void* fn : {(const void*)lstm_tc_kernel<8>, (const void*)lstm_tc_kernel<16>}) {
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: func attributes: %s", cudaGetErrorString(e)); return (int)e; }
@@ -371,8 +380,10 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
 
     const int clusters = (d->batch + nbv - 1) / nbv;
     cudaLaunchConfig_t cfg{};
+    static int epi_warps = 0;
+    if (!epi_warps) { const char* env = getenv("AC_LSTM_EPI_WARPS"); epi_warps = (env && atoi(env) == 8) ? 8 : 16; }
     cfg.gridDim = dim3(clusters * CL);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(64 + 32 * epi_warps);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -382,7 +393,8 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_kernel, (const __nv_bfloat16*)d->w_hh_bf16, p);
+    cudaError_t e = epi_warps == 8 ? cudaLaunchKernelEx(&cfg, lstm_tc_kernel<8>, (const __nv_bfloat16*)d->w_hh_bf16, p)
+                                   : cudaLaunchKernelEx(&cfg, lstm_tc_kernel<16>, (const __nv_bfloat16*)d->w_hh_bf16, p);
     ac::count_launch();
     if (e != cudaSuccess) { ac::set_error("ac_lstm_tc: launch: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
