@@ -167,7 +167,11 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             clip_base[g] = G * base + (G < rem ? G : rem);
         }
     }
-    const uint32_t tx_bytes[2] = {CL * (p.trim ? 4u * ng[0] * 16u : SLICE_BYTES), CL * (p.trim ? 4u * ng[1] * 16u : SLICE_BYTES)};
+    // bytes one source CTA pushes per group and step: the whole 512-byte slice (trim 0), rows [0, n) of each of its four core
+    // matrices (trim 1: four copies of n*16 bytes), or two copies that each span two core matrices up to row n of the second
+    // (trim 3: 128 + n*16 bytes; the unused rows of the first travel along)
+    auto slice_tx = [&](int n) { return p.trim == 1 ? 4u * n * 16u : (p.trim == 3 ? 2u * (128u + n * 16u) : SLICE_BYTES); };
+    const uint32_t tx_bytes[2] = {CL * slice_tx(ng[0]), CL * slice_tx(ng[1])};
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&h_ready[i], 1);
@@ -290,10 +294,10 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             // destinations of this CTA's slice of the group: the eight warps cover the 16 peers, lane l < 2 of warp w pushes the
             // 512-byte slice to peer 2*(w % 8) + l.  (Trimmed: lane l < 8 pushes rows [0, n) of core matrix l & 3 to peer 2*(w%8) + (l>>2).)
             const int w8 = ew & 7;
-            const uint32_t dst_rank = (uint32_t)(w8 * 2 + (p.trim ? (lane >> 2) & 1 : lane & 1));
-            const uint32_t piece = p.trim ? (uint32_t)(lane & 3) * 128u : 0u;
-            const uint32_t copy_bytes = p.trim ? (uint32_t)n * 16u : SLICE_BYTES;
-            const bool sender = lane < (p.trim ? 8 : 2);
+            const uint32_t dst_rank = (uint32_t)(w8 * 2 + (p.trim == 1 ? (lane >> 2) & 1 : (p.trim == 3 ? (lane >> 1) & 1 : lane & 1)));
+            const uint32_t piece = p.trim == 1 ? (uint32_t)(lane & 3) * 128u : (p.trim == 3 ? (uint32_t)(lane & 1) * 256u : 0u);
+            const uint32_t copy_bytes = p.trim == 1 ? (uint32_t)n * 16u : (p.trim == 3 ? 128u + (uint32_t)n * 16u : SLICE_BYTES);
+            const bool sender = lane < (p.trim == 1 ? 8 : (p.trim == 3 ? 4 : 2));
             const uint32_t peer_b = map_to_cta(smem_u32(b_s) + grp * G_BYTES + rank * SLICE_BYTES + piece, dst_rank);
             const uint32_t peer_bar = map_to_cta(smem_u32(&h_ready[grp]), dst_rank);
             load_pre(0);
