@@ -67,6 +67,7 @@ struct LstmTcParams {
     long long skip_bs, fin_bs;
     int fin_act, batch, steps;
     int n_groups;  // clip groups over the whole launch (two per cluster); group G takes batch/n_groups clips (+1 for the first batch%n_groups)
+    int poll;      // every epilogue warp polls the accumulator barrier itself (else one per group does and releases the rest)
     int trim;      // push only the operand rows of clips that exist (4 copies of ng*16 bytes per peer instead of one of 512)
     int f16;    // operands (W_hh in tensor memory, h in shared memory) are fp16 instead of bf16
     int out_f16, skip_f16;  // hi-plane formats of out / final and of skip (lo planes are bf16)
@@ -251,6 +252,7 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
         const int q = warp & 3;            // TMEM lane quarter == gate index (rows q*32 + u)
         const int grp = ew >> 3;           // clip group of this warp
         const int sub = (ew >> 2) & 1;     // which 4 of the group's 8 operand rows this warp activates
+        const int w8 = ew & 7;             // warp index inside the group
         const int n = ng[grp], cb = clip_base[grp];
         const int u = lane;
         const int gu = (int)rank * UPC + u;
@@ -293,7 +295,6 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
             };
             // destinations of this CTA's slice of the group: the eight warps cover the 16 peers, lane l < 2 of warp w pushes the
             // 512-byte slice to peer 2*(w % 8) + l.  (Trimmed: lane l < 8 pushes rows [0, n) of core matrix l & 3 to peer 2*(w%8) + (l>>2).)
-            const int w8 = ew & 7;
             const uint32_t dst_rank = (uint32_t)(w8 * 2 + (p.trim == 1 ? (lane >> 2) & 1 : (p.trim == 3 ? (lane >> 1) & 1 : lane & 1)));
             const uint32_t piece = p.trim == 1 ? (uint32_t)(lane & 3) * 128u : (p.trim == 3 ? (uint32_t)(lane & 1) * 256u : 0u);
             const uint32_t copy_bytes = p.trim == 1 ? (uint32_t)n * 16u : (p.trim == 3 ? 128u + (uint32_t)n * 16u : SLICE_BYTES);
@@ -308,7 +309,10 @@ lstm_tc_kernel(const __nv_bfloat16* __restrict__ w_hh, const LstmTcParams p) {
                 if (t + 1 < p.steps) load_pre(t + 1);  // in flight during this step's MMA
                 if (t > 0) emit(t - 1);
                 if (dbg) p.dbg[t * 8 + 0] = clock64();
-                mbar_wait(&d_full[grp], t & 1);
+                // p.poll = 0 (AC_LSTM_POLL=0): one warp of the group polls the accumulator barrier and the other seven sleep in the
+                // hardware barrier -- tried against the power cap: +70 cycles per step, no measurable effect on the step
+                if (p.poll || w8 == 0) mbar_wait(&d_full[grp], t & 1);
+                if (!p.poll) grp_bar_sync(grp);
                 tc_fence_after();
                 if (dbg) p.dbg[t * 8 + 1] = clock64();
                 uint32_t v[HC];
@@ -411,12 +415,15 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     p.f16 = d->operand_fp16 ? 1 : 0;
     p.out_f16 = d->out_fp16 ? 1 : 0; p.skip_f16 = d->skip_fp16 ? 1 : 0;
 
-    // Co-resident clusters (7 on a B200): a batch is spread over as many clusters as one wave holds -- fewer clips per
-    // cluster means fewer bytes in each step's all-gather and less gate math per thread -- in whole waves beyond that.
+    // Clusters per wave.  7 are co-resident on a B200 and a lone layer is fastest spread over all of them (0.852 ms at 64 clips:
+    // 4-5 clips per group) -- but inside the power-capped step the same layer takes ~0.89 ms either way (the chain scales with
+    // the SM clock) and 112 busy SMs instead of 64 cost the FOLLOWING kernels 1-2 % of clock: A/B of the whole step on one
+    // box, twice on two boxes: 16.50 / 16.55 ms with 4 clusters against 16.76 / 16.77 ms with 7.  So 4 is the default
+    // (AC_LSTM_CLUSTERS=0: ask the occupancy API, =n: n).
     static int max_clusters = 0;
     if (!max_clusters) {
         const char* env = getenv("AC_LSTM_CLUSTERS");
-        int n = env ? atoi(env) : 0;
+        int n = env ? atoi(env) : 4;
         if (n <= 0) {
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(CL * 16); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = smem;
@@ -436,6 +443,9 @@ extern "C" int ac_lstm_tc(const ac_lstm_tc_desc* d, void* stream) {
     // 512-byte slice in one copy is faster (measured: 0.852 vs 0.882 ms at 4-5 clips per group, 0.942 vs 0.888 ms at 8)
     static int trim = -1;
     if (trim < 0) { const char* env = getenv("AC_LSTM_TRIM"); trim = env ? atoi(env) : 2; }
+    static int poll = -1;
+    if (poll < 0) { const char* env = getenv("AC_LSTM_POLL"); poll = env ? atoi(env) : 1; }
+    p.poll = poll;
     p.trim = trim == 2 ? ((d->batch + p.n_groups - 1) / p.n_groups <= 6 ? 1 : 0) : trim;
 
     cudaLaunchConfig_t cfg{};
