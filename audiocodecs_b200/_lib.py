@@ -8,7 +8,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaudiocodecs_b200.so")
+LIB_PATH = os.environ.get("AC_LIB_PATH") or os.path.join(_HERE, "lib", "libaudiocodecs_b200.so")   # AC_LIB_PATH: A/B a second build
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "audiocodecs_b200.h")
 
 c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p

@@ -118,12 +118,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
@@ -133,7 +134,9 @@ class ClockSampler:
         # "under load" = upper half of the samples (the sampler also sees the idle edges)
         load = sm[len(sm) // 2:] if sm else []
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        pw.sort()
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": pw[-1] if pw else None}   # board power: the step runs at the 1000 W cap (sw_power_cap), see DESIGN.md
 
 
 class Ctx:
