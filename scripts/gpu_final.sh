@@ -10,4 +10,4 @@ for spec in "encodec exact 64" "encodec fp16 64" "dac exact 64" "dac fp16 64" "m
   AC_PRECISION=$2 timeout 400 python scripts/layer_times.py $1 $3 10 > gpurun_out/r02_layers_$1_$2.txt 2>&1
   echo "$(grep '^total' gpurun_out/r02_layers_$1_$2.txt || tail -2 gpurun_out/r02_layers_$1_$2.txt)"
 done
-bash scripts/gpu_r2m.sh > gpurun_out/r02_ncu_lists.log 2>&1; tail -3 gpurun_out/r02_ncu_lists.log
+bash scripts/gpu_ncu_lists.sh > gpurun_out/r02_ncu_lists.log 2>&1; tail -3 gpurun_out/r02_ncu_lists.log
