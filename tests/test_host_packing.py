@@ -162,6 +162,9 @@ def test_autotune_skips_and_reports(monkeypatch):
     assert [e[1] for e in tc.TUNE_ERRORS] == ["broken"]
     calls.clear()
     assert tc.autotune(("k", 1), vs) == "fast" and calls == ["fast"]            # cached: straight to the winner
+    # a near-tie (within 3 %) goes to the variant listed first; a clear win does not
+    assert tc.autotune(("k", 4), [variant("fused", 1.02), variant("unfused", 1.0)]) == "fused"
+    assert tc.autotune(("k", 5), [variant("fused", 1.10), variant("unfused", 1.0)]) == "unfused"
     monkeypatch.setattr(tc, "TUNE", False)
     assert tc.autotune(("k", 2), vs) == "slow"                                   # no tuning: the first variant that launches
     with pytest.raises(RuntimeError, match="no variant"):
