@@ -26,7 +26,7 @@ FUSED_MAX_CH = int(__import__("os").environ.get("AC_FUSED_MAX_CH", "64"))   # re
                        # 0.35 vs 0.40 ms (fp16) / 0.76 vs 0.85 ms (exact) -- 0.07 ms of a 17.4 ms step in the bench loop, not worth
                        # re-grouping the encoder's accumulation -- and at 256 it loses (0.65-0.80 vs 0.48 ms exact).  A rule, not a timing: the two forms group
                        # the fp32 accumulation differently, so the choice must not depend on the batch size.  None = let the
-                       # tuner time one against the other (scripts/tune_report.py)
+                       # tuner time one against the other (AC_TUNE_FUSION=1 python scripts/layer_times.py)
 _VALID_BW = (1.5, 3.0, 6.0, 12.0, 24.0)
 
 

@@ -299,7 +299,7 @@ def resunit_tc(W1: TcWeights, W2: TcWeights, a: Src, m_rows, *, x: Act = None, r
 _TUNED = {}
 TUNE = True  # False: always take the first variant
 TUNE_ERRORS = []  # (key, variant, message) of variants that failed with something other than a configuration error
-TUNE_LOG = []     # (key, {variant: best ms}) of every tuned key, for reports (scripts/tune_report.py)
+TUNE_LOG = []     # (key, {variant: best ms}) of every tuned key, for reports (scripts/layer_times.py prints it)
 
 
 def autotune(key, variants):
