@@ -68,7 +68,7 @@ def test_end_to_end_code_match_report(encodec_sd, dev):
 
 
 @pytest.mark.parametrize("op_dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12), (70, 9)])
+@pytest.mark.parametrize("B,T", [(16, 40), (5, 33), (37, 12), (70, 9), (1, 25), (2, 1), (3, 7), (130, 5)])   # lone clip, one step, odd groups, several waves
 def test_lstm_tc_cluster_kernel(encodec_sd, dev, B, T, op_dtype, tol):
     """tcgen05 cluster LSTM (fp16 -- the shipped configuration -- or bf16 W_hh and h operands, fp32 accumulate / cell state)
     vs the oracle's explicit loop."""
