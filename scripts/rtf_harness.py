@@ -13,8 +13,8 @@ secs = float(sys.argv[1]) if len(sys.argv) > 1 else 15.86  # length of R/audioco
 dev = torch.device("cuda:0")
 codecs = {
     "encodec": A.Encodec(16000, 24000, num_codebooks=8, state_dict=weights.encodec_state_dict(0)),
-    "dac": A.DAC(16000, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0), precision="bf16"),
-    "mimi": A.Mimi(16000, num_codebooks=8, state_dict=weights.mimi_state_dict(0), precision="bf16"),
+    "dac": A.DAC(16000, 44100, num_codebooks=9, state_dict=weights.dac_state_dict(0)),
+    "mimi": A.Mimi(16000, num_codebooks=8, state_dict=weights.mimi_state_dict(0)),
 }
 sig = (torch.randn(1, int(16000 * secs), generator=torch.Generator().manual_seed(0)) * 0.1).to(dev)
 for name, codec in codecs.items():
