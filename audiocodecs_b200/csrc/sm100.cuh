@@ -73,7 +73,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (AC_MBAR_SUSPEND_NS > 0 ? (1u << 17) : (1u << 24))) __trap();   // ~2.7 s either way (20 us / ~160 ns per failed poll)
+        // a protocol bug traps after >= 0.17 s (hinted: 2^20 polls of 160 ns .. 20 us each, whatever the hardware makes of the
+        // hint) / ~2.7 s (plain: 2^24 polls); legitimate waits inside these kernels last one tile -- microseconds
+        if (++spins > (AC_MBAR_SUSPEND_NS > 0 ? (1u << 20) : (1u << 24))) __trap();
     }
 }
 
