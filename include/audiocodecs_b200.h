@@ -92,8 +92,9 @@ AC_API int ac_lstm_layer_f32(const float* pre, const float* w_hh, const float* s
 
 
 /*
- * Tensor-core LSTM layer recurrence (hidden = 512): one cluster of 16 CTAs per 16 clips, W_hh (bf16) resident in
- * shared memory, h exchanged through distributed shared memory, one tcgen05.mma chain per step (see csrc/lstm_tc.cu).
+ * Tensor-core LSTM layer recurrence (hidden = 512): clusters of 16 CTAs, each taking up to 16 clips as two independently
+ * pipelined groups of <= 8; W_hh (16-bit) resident in TENSOR memory as the A operand, h exchanged through distributed shared
+ * memory by bulk copies, one tcgen05.mma chain per group and step (see csrc/lstm_tc.cu).  Any batch size (waves of clusters).
  * pre [B][T][4*hidden] fp32 holds W_ih x + b_ih + b_hh (ac_conv_tc with y32).  Outputs: bf16 h planes (hi [+lo]) for
  * the next layer's input GEMM, and/or final = act(h + skip) planes in a haloed activation buffer.
  * Replaces EncodecLSTM (HF/encodec:236-249).
