@@ -54,3 +54,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_config_error_is_a_runtime_error():
     assert issubclass(_lib.ConfigError, RuntimeError)
+
+
+def test_library_sass_uses_tcgen05_tmem_tma():
+    """the shipped library is real sm_100a code: tcgen05.mma (UTCHMMA), tensor-memory loads / stores (LDTM / STTM), TMA tensor
+    loads and stores (UTMALDG / UTMASTG) and bulk DSMEM copies (UBLKCP) are in its SASS; the tap-GEMM kernels address shared
+    memory with LDS / STS, not generic loads (the round-2 instruction diet)."""
+    import shutil
+    import subprocess
+    from audiocodecs_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for op in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS"):
+        assert op in sass, op
+    # per kernel: no generic LD.E / ST.E in the two tap-GEMM kernels
+    cur, generic = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+        elif cur and ("conv_tc_kernel" in cur or "resunit_tc_kernel" in cur) and (" LD.E" in line or " ST.E" in line):
+            generic[cur] = generic.get(cur, 0) + 1
+    assert not generic, generic
